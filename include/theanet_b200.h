@@ -1,0 +1,195 @@
+/* theanet_b200 -- C ABI of the B200 (sm_100a) kernels behind theanet's CNN-training hot path.
+ *
+ * The reference (rakeshvar/theanet) has no FFI: its "operator API" is the set of Theano ops each
+ * layer asks for.  Every entry point below replaces one such call site (cited as
+ * <reference file>:<line>) and is what theanet_b200/_C.py binds with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative TN_ERR_* code; tn_last_error() gives the
+ *     message of the last failure on the calling thread;
+ *   - all pointers are DEVICE pointers owned by the caller unless the name ends in _host; the
+ *     library never allocates or frees caller memory and never synchronises;
+ *   - `stream` is a cudaStream_t passed as void*; all launches are asynchronous and legal inside
+ *     CUDA-graph capture;
+ *   - activations are NCHW float32, conv filters OIHW, dense weights (n_in, n_out) row-major --
+ *     the layouts theanet's .pkl exposes (theanet/neuralnet.py:298-301);
+ *   - `ctl` is a device int32[TN_CTL_WORDS] control block the host refreshes once per step (so a
+ *     captured graph can be replayed): see TN_CTL_*.
+ */
+#ifndef THEANET_B200_H
+#define THEANET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TN_VERSION 100
+
+enum {
+  TN_OK = 0,
+  TN_ERR_ARG = -1,
+  TN_ERR_SHAPE = -2,
+  TN_ERR_ALIGN = -3,
+  TN_ERR_CUDA = -4,
+  TN_ERR_UNSUPPORTED = -5
+};
+
+/* activation kinds -- theanet/layer/layer.py:27-39 */
+enum {
+  TN_ACT_LINEAR = 0,
+  TN_ACT_RELU = 1,        /* max(0,x) */
+  TN_ACT_LEAKY = 2,       /* reluNN: max(0,x) + (min(0,x)*NN)/100, NN in act_nn */
+  TN_ACT_TANH = 3,
+  TN_ACT_SCALED_TANH = 4, /* 1.7*tanh(2x/3) */
+  TN_ACT_SIGMOID = 5,
+  TN_ACT_SOFTPLUS = 6
+};
+
+/* control block words (device int32[TN_CTL_WORDS]) */
+enum {
+  TN_CTL_STEP = 0,     /* Philox step counter */
+  TN_CTL_SAMPLE0 = 1,  /* global index (within the minibatch stream) of this shard's first sample */
+  TN_CTL_ROW0 = 2,     /* first corpus row of this shard when slicing x[i*B:(i+1)*B] */
+  TN_CTL_LR_BITS = 3,  /* float32 learning rate, bit pattern */
+  TN_CTL_WORDS = 8
+};
+
+/* Philox stream purposes (counter word 3) -- see DESIGN.md "Randomness" */
+enum { TN_RNG_DROPOUT = 0, TN_RNG_FLIP = 1, TN_RNG_NOISE = 2, TN_RNG_SCALARS = 3 };
+
+int tn_version(void);
+const char *tn_last_error(void);
+/* refuses anything that is not compute capability 10.x */
+int tn_device_check(int device);
+
+/* ---- randomness (replaces theano RandomStreams: dropout.py:10-12, inlayers.py:72-141) -------- */
+/* words[s*n + j] = Philox4x32-10 word j of sample (sample0+s); used by tests to pin the stream */
+int tn_philox_words(uint32_t *words, int n_samples, int n_per_sample, uint64_t seed, int purpose,
+                    int step, int sample0, void *stream);
+
+/* ---- ElasticLayer (theanet/layer/inlayers.py:29-163) -------------------------------------- */
+typedef struct tn_elastic_prm {
+  int h;              /* img_sz (square) */
+  int sigma;          /* gaussian half-width; table is (2*sigma+1)^2 */
+  float translation;  /* 0 = off */
+  float magnitude;    /* 0 = off */
+  float log_zoom;     /* float32(ln zoom); 0 = off */
+  float angle_rad;    /* float32(angle*pi/180); 0 = off */
+  int zoom_on;        /* zoom != 1 */
+  int nearest;        /* 1: iround gather (inlayers.py:124-127), 0: bilinear (:129-137) */
+  double clip_hi;     /* h - 1 - .001 (inlayers.py:121-122) */
+} tn_elastic_prm;
+
+/* noise[2*h*h] ~ N(0,1) float32, Box-Muller on the (seed, step) Philox stream (inlayers.py:94) */
+int tn_elastic_noise(float *noise, int h, uint64_t seed, const int32_t *ctl, void *stream);
+/* The per-minibatch sampling grid (inlayers.py:77-122).  u_inj: 8 injected uniforms or NULL (then
+ * drawn from the (seed, step) stream).  filt: the (2*sigma+1)^2 float32 table (inlayers.py:87-91).
+ * Outputs: target[2*h*h] float64 before clipping (debugout, may be NULL), tyx[2*h*h] float64
+ * clipped coordinates (may be NULL), gidx[h*h] int32 gather base (row*h+col), gfrac[2*h*h]
+ * float32 (fy, fx) -- written only when !nearest. */
+int tn_elastic_field(const tn_elastic_prm *prm_host, const float *noise, const float *u_inj,
+                     const float *filt, uint64_t seed, const int32_t *ctl, double *target,
+                     double *tyx, int32_t *gidx, float *gfrac, void *stream);
+/* Batch loader + warp (inlayers.py:63-64,124-142): out[b] = flip(gather(invert(src[row(b)]))).
+ * row(b) = idx ? idx[b] : ctl[ROW0] + b.  mode 0 = no gather (identity grid), 1 = nearest,
+ * 2 = bilinear.  pflip > 0 draws the per-pixel Bernoulli mask from the Philox stream unless
+ * flip_inj (B*C*h*h float32 0/1) is given. */
+int tn_elastic_warp(const float *corpus, const int32_t *idx, const int32_t *ctl, int B, int C,
+                    int h, int invert, int mode, const int32_t *gidx, const float *gfrac,
+                    double pflip, const float *flip_inj, uint64_t seed, float *out, void *stream);
+
+/* ---- ConvLayer (theanet/layer/convpool.py:14-95; nnet.conv2d :54-56, filter flipped) -------- */
+/* out[b,m,i,j] = act(bias[m] + sum_{c,u,v} xpad[b,c,i+u,j+v] * W[m,c,f-1-u,f-1-v]); stride 1;
+ * pad_lo zeros before, whatever is needed after (valid: 0, same: f-1-(f-1)/2). */
+int tn_conv2d_fprop(const float *x, const float *W, const float *bias, float *out, int B, int C,
+                    int S, int M, int f, int pad_lo, int out_sz, int act, int act_nn,
+                    void *stream);
+/* dx[b,c,y,x] = sum_{m,u,v} gz[...] * W[...] (gradient wrt the layer input; tt.grad layer.py:83).
+ * If x_in != NULL the result is multiplied by act'(x_in) of the PREVIOUS layer's activation
+ * (act_prev / nn_prev), i.e. it directly yields dL/dz of a conv layer feeding this one. */
+int tn_conv2d_dgrad(const float *gz, const float *W, float *dx, const float *x_in, int B, int C,
+                    int S, int M, int f, int pad_lo, int out_sz, int act_prev, int nn_prev,
+                    void *stream);
+size_t tn_conv2d_wgrad_workspace_bytes(int B, int C, int S, int M, int f);
+/* dW (OIHW) and db from the layer input x and dL/dz; deterministic two-stage reduction through
+ * `workspace` (>= tn_conv2d_wgrad_workspace_bytes). */
+int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float *db, void *workspace, int B,
+                    int C, int S, int M, int f, int pad_lo, int out_sz, void *stream);
+
+/* ---- PoolLayer (theanet/layer/convpool.py:97-127; pool_2d max, stride = window) ------------- */
+/* planes = B*C; out_sz = ceil(S/p) (ignore_border=False) or S/p */
+int tn_maxpool_fwd(const float *x, float *out, int planes, int S, int p, int out_sz,
+                   void *stream);
+/* dx = (x == out[window]) ? dout[window] : 0  -- every tied maximum receives the gradient
+ * (Theano MaxPoolGrad) -- then times act'(x) of the layer that produced x (fused dL/dz). */
+int tn_maxpool_bwd(const float *dout, const float *x, const float *out, float *dx, int planes,
+                   int S, int p, int out_sz, int act, int act_nn, void *stream);
+
+/* ---- HiddenLayer / DropOutLayer (theanet/layer/hidden.py:11-54, dropout.py:9-31) ------------ */
+/* out = act(x.W + b) * mask * out_scale.  mask ~ Bernoulli(pkeep) per (global sample, unit) from
+ * the (seed, step) stream (pkeep >= 1: none); mask_inj (B*n_out float32) overrides the stream.
+ * out_scale = 1-pdrop for the test twin (hidden.py:50-55), 1 otherwise. */
+int tn_dense_fwd(const float *x, const float *W, const float *bias, float *out, int B, int n_in,
+                 int n_out, int act, int act_nn, double pkeep, uint64_t seed, const int32_t *ctl,
+                 const float *mask_inj, float out_scale, void *stream);
+/* dx = g.W^T; if prev_out != NULL it is turned into dL/dz of the previous dense layer:
+ * dx *= mask_prev * act_prev'(prev_out) (prev_out = that layer's stored, masked output). */
+int tn_dense_bwd_data(const float *g, const float *W, float *dx, int B, int n_in, int n_out,
+                      const float *prev_out, int act_prev, int nn_prev, double pkeep_prev,
+                      uint64_t seed_prev, const int32_t *ctl, const float *mask_inj_prev,
+                      void *stream);
+/* dW = x^T.g, db = column sums of g */
+int tn_dense_bwd_weights(const float *x, const float *g, float *dW, float *db, int B, int n_in,
+                         int n_out, void *stream);
+/* standalone dropout / test-time scaling: out = x * mask * scale (also used on gradients) */
+int tn_dropout_apply(const float *x, float *out, int B, int n, double pkeep, uint64_t seed,
+                     const int32_t *ctl, const float *mask_inj, float scale, void *stream);
+/* dL/dz = g * act'(a) for a layer whose stored output is a (conv directly followed by dense) */
+int tn_act_bwd(const float *g, const float *a, float *gz, int64_t n, int act, int act_nn,
+               void *stream);
+
+/* ---- SoftmaxLayer + NLL (theanet/layer/outlayers.py:50-51,69-80,83-102) ---------------------- */
+/* labels: y[row(b)] with row(b) as in tn_elastic_warp.  logprob = log softmax(z);
+ * rowloss[b] = -logprob[b,y_b]; g = (softmax - onehot) * inv_global_batch. */
+int tn_softmax_nll_fwd_bwd(const float *z, const int32_t *y, const int32_t *idx,
+                           const int32_t *ctl, int B, int n, float inv_global_batch,
+                           float *logprob, float *g, float *rowloss, void *stream);
+/* test twin: logprob, preds = argmax (first maximum, int64), stats[0] = mean(pred != y),
+ * stats[1] = mean(p[y])  (outlayers.py:69-80) */
+int tn_softmax_test_stats(const float *z, const int32_t *y, const int32_t *idx,
+                          const int32_t *ctl, int B, int n, float *logprob, int64_t *preds,
+                          float *stats, void *stream);
+
+/* ---- Layer.get_updates / get_wtcost (theanet/layer/layer.py:70-117) ------------------------- */
+typedef struct tn_param_seg {
+  int64_t offset;   /* element offset into the flat theta / velocity / gradient buffers */
+  int64_t size;
+  int32_t ndim;     /* 1, 2 (rows x cols, norm over axis 0) or 4 (rows = out kernels) */
+  int32_t rows;
+  int32_t cols;
+  float momentum;
+  float rate;       /* 0 freezes the tensor (layer.py:74-75) */
+  float maxnorm;    /* 0 = off */
+  float l1;
+  float l2;
+} tn_param_seg;
+
+size_t tn_update_workspace_bytes(int nseg, int64_t total);
+/* One step for all tensors: g' = g*grad_scale + L1*sgn(theta) + 2*L2*theta;
+ * v' = m*v + (1-m)*g'; theta' = theta - rate*lr*v (OLD v); maxnorm on theta'.
+ * cost_out[0] = (sum(rowloss[0..n_rowloss)) or nll_sum[0]) * nll_scale + L1/L2 weight cost of the
+ * PRE-update theta.  segs_host is copied into the launch (<= 64 segments). lr comes from ctl. */
+int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
+                                   const tn_param_seg *segs_host, int nseg, int64_t total,
+                                   const int32_t *ctl, float grad_scale, const float *nll_sum,
+                                   float nll_scale, float *cost_out, void *workspace,
+                                   void *stream);
+/* nll_sum[0] = sum_b rowloss[b] (fixed order, deterministic) */
+int tn_reduce_rowloss(const float *rowloss, int B, float *nll_sum, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,456 @@
+"""Per-kernel parity: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for integer / index / comparison work (Philox words, gather indices, nearest and
+bilinear warps, pool forward / tie routing, argmax); for float32 arithmetic whose summation order
+differs from numpy's, max|a-b| / max|b| <= 1e-3 per tensor (north_star tolerance) -- in practice
+these agree to ~1e-6."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox
+from oracle import theanet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope='module')
+def C():
+    from theanet_b200 import _C
+    assert torch.cuda.is_available()
+    _C.check(_C.lib.tn_device_check(0), 'tn_device_check')
+    return _C
+
+
+def dev(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda()
+
+
+def make_ctl(C, step=0, sample0=0, row0=0, lr=0.1):
+    c = np.zeros(C.CTL_WORDS, np.int32)
+    c[C.CTL_STEP], c[C.CTL_SAMPLE0], c[C.CTL_ROW0] = step, sample0, row0
+    c[C.CTL_LR_BITS] = np.float32(lr).view(np.int32)
+    return dev(c)
+
+
+def sync():
+    torch.cuda.synchronize()
+
+
+# --------------------------------------------------------------------------------------------
+def test_philox_words_bit_exact(C):
+    for n, ns, seed, purpose, step, s0 in [(500, 7, 802165, 0, 3, 40), (784, 5, 2 ** 40 + 17, 1, 0, 0),
+                                           (13, 3, 1, 2, 2 ** 31 - 1, 1000)]:
+        w = torch.zeros((ns, n), dtype=torch.int32, device='cuda')
+        C.call('tn_philox_words', C.ptr(w), ns, n, seed, purpose, step, s0, None)
+        sync()
+        want = philox.random_words(seed, purpose, step, np.arange(s0, s0 + ns), n)
+        assert np.array_equal(w.cpu().numpy().view(np.uint32), want)
+
+
+def elastic_prm(C, h, args):
+    p = C.ElasticPrm()
+    p.h, p.sigma = h, int(args.get('sigma', 1))
+    p.translation, p.magnitude = float(args.get('translation', 0)), float(args.get('magnitude', 0))
+    zoom = args.get('zoom', 1)
+    p.zoom_on = int(zoom != 1)
+    p.log_zoom = float(np.float32(np.log(zoom)))
+    p.angle_rad = float(np.float32(args.get('angle', 0) * np.pi / 180))
+    p.nearest = int(bool(args.get('nearest', False)))
+    p.clip_hi = h - 1 - .001
+    return p
+
+
+def test_elastic_noise_matches_oracle_stream(C):
+    h, seed, step = 28, 426405, 5
+    noise = torch.zeros(2 * h * h, device='cuda')
+    C.call('tn_elastic_noise', C.ptr(noise), h, seed, C.ptr(make_ctl(C, step=step)), None)
+    sync()
+    want = philox.elastic_noise(seed, step, 2 * h * h)
+    got = noise.cpu().numpy()
+    # float64 log/sincos on the device may differ from libm in the last ulp before the float32
+    # rounding; equality is expected for (nearly) every value
+    assert np.mean(got == want) > 0.999
+    assert np.allclose(got, want, rtol=3e-7, atol=0)
+
+
+ELASTIC_CASES = [
+    dict(translation=2, zoom=1.1, magnitude=60, sigma=15, angle=5, nearest=True),
+    dict(translation=2, zoom=1.1, magnitude=20, sigma=5, angle=5, nearest=False),
+    dict(translation=3, nearest=True),
+    dict(zoom=1.3, nearest=False),
+    dict(angle=20, nearest=True),
+    dict(magnitude=30, sigma=4, nearest=False),
+]
+
+
+@pytest.mark.parametrize('case', range(len(ELASTIC_CASES)))
+@pytest.mark.parametrize('h', [28, 33])
+def test_elastic_field_and_warp_bit_exact(C, case, h):
+    args = ELASTIC_CASES[case]
+    rng = np.random.default_rng(100 + case)
+    noise = rng.standard_normal((2, h, h)).astype(np.float32)
+    u = rng.uniform(0, 1, 8).astype(np.float32)
+    ty, tx, disp = O.elastic_target(h, args, noise, u)
+    prm = elastic_prm(C, h, args)
+    sigma = int(args.get('sigma', 1))
+    filt = dev(O.gaussian_filter(sigma)) if args.get('magnitude', 0) else None
+    target = torch.zeros(2 * h * h, dtype=torch.float64, device='cuda')
+    tyx = torch.zeros(2 * h * h, dtype=torch.float64, device='cuda')
+    gidx = torch.zeros(h * h, dtype=torch.int32, device='cuda')
+    gfrac = torch.zeros(2 * h * h, device='cuda')
+    C.call('tn_elastic_field', ctypes.byref(prm), C.ptr(dev(noise)), C.ptr(dev(u)), C.ptr(filt), 0,
+           None, C.ptr(target), C.ptr(tyx), C.ptr(gidx), C.ptr(gfrac), None)
+    sync()
+    got = tyx.cpu().numpy().reshape(2, h, h)
+    assert np.max(np.abs(got[0] - ty)) < 1e-9 and np.max(np.abs(got[1] - tx)) < 1e-9
+    assert np.max(np.abs(target.cpu().numpy().reshape(2, h, h) - np.indices((h, h)) - disp)) < 1e-9
+    if args.get('nearest'):
+        want_idx = O._iround(ty) * h + O._iround(tx)
+    else:
+        want_idx = ty.astype(np.int32) * h + tx.astype(np.int32)
+    assert np.array_equal(gidx.cpu().numpy().reshape(h, h), want_idx)
+    # warp: B images, C_ maps, invert + flip noise from the Philox stream, bit-exact
+    B, C_ = 5, 2
+    x = rng.uniform(0, 1, (B + 3, C_, h, h)).astype(np.float32)
+    x *= (x > .5)
+    seed, step, s0, row0, pflip = 99, 4, 64, 2, 0.03
+    out = torch.zeros((B, C_, h, h), device='cuda')
+    ctl = make_ctl(C, step=step, sample0=s0, row0=row0)
+    C.call('tn_elastic_warp', C.ptr(dev(x)), None, C.ptr(ctl), B, C_, h, 1,
+           1 if args.get('nearest') else 2, C.ptr(gidx), C.ptr(gfrac), pflip, None, seed,
+           C.ptr(out), None)
+    sync()
+    fm = philox.bernoulli_mask(seed, philox.PURPOSE_FLIP, step, np.arange(s0, s0 + B), C_ * h * h,
+                               pflip).reshape(B, C_, h, h)
+    want = O.elastic_apply(x[row0:row0 + B], dict(args, invert_image=True), ty, tx, fm)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+def test_elastic_warp_identity_index_list_and_injected_flip(C):
+    rng = np.random.default_rng(7)
+    B, C_, h = 6, 3, 9         # C*h*h = 243: exercises the non-multiple-of-4 tail
+    x = rng.uniform(0, 1, (20, C_, h, h)).astype(np.float32)
+    idx = rng.integers(0, 20, B).astype(np.int32)
+    fm = (rng.uniform(0, 1, (B, C_, h, h)) < .2).astype(np.float32)
+    out = torch.zeros((B, C_, h, h), device='cuda')
+    C.call('tn_elastic_warp', C.ptr(dev(x)), C.ptr(dev(idx)), C.ptr(make_ctl(C)), B, C_, h, 0, 0,
+           None, None, 0.0, C.ptr(dev(fm)), 0, C.ptr(out), None)
+    sync()
+    want = O.elastic_apply(x[idx], {}, None, None, fm)
+    assert np.array_equal(out.cpu().numpy(), want)
+
+
+# --------------------------------------------------------------------------------------------
+CONV_CASES = [  # B, C, S, M, f, mode, act
+    (6, 1, 28, 4, 3, 'valid', 'relu10'),
+    (6, 4, 13, 20, 3, 'valid', 'relu05'),
+    (3, 3, 12, 7, 3, 'same', 'relu05'),
+    (3, 2, 11, 5, 5, 'valid', 'tanh'),
+    (2, 3, 9, 6, 4, 'same', 'relu'),
+    (2, 5, 10, 9, 2, 'valid', 'linear'),
+    (2, 1, 64, 4, 3, 'valid', 'relu10'),
+    (2, 20, 31, 20, 3, 'same', 'relu05'),
+]
+
+
+@pytest.mark.parametrize('case', range(len(CONV_CASES)))
+def test_conv_fprop_dgrad_wgrad(C, case):
+    B, Cin, S, M, f, mode, actn = CONV_CASES[case]
+    rng = np.random.default_rng(200 + case)
+    x = rng.standard_normal((B, Cin, S, S)).astype(np.float32)
+    W = (rng.standard_normal((M, Cin, f, f)) / np.sqrt(Cin * f * f)).astype(np.float32)
+    b = rng.standard_normal(M).astype(np.float32)
+    pad_lo, out_sz = O.conv_geometry(S, f, mode)
+    z, cache = O.conv_forward(x, W, mode)
+    a = O.act_forward(actn, z + b[None, :, None, None])
+    act, nn = C.act_code(actn)
+    xd, Wd, bd = dev(x), dev(W), dev(b)
+    out = torch.zeros((B, M, out_sz, out_sz), device='cuda')
+    C.call('tn_conv2d_fprop', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(out), B, Cin, S, M, f, pad_lo,
+           out_sz, act, nn, None)
+    sync()
+    assert rel(out.cpu().numpy(), a) < 1e-5
+    gz = rng.standard_normal(z.shape).astype(np.float32)
+    dW, db, dx = O.conv_backward(gz, W, cache)
+    gzd = dev(gz)
+    dxd = torch.zeros_like(xd)
+    C.call('tn_conv2d_dgrad', C.ptr(gzd), C.ptr(Wd), C.ptr(dxd), None, B, Cin, S, M, f, pad_lo,
+           out_sz, 0, 0, None)
+    sync()
+    assert rel(dxd.cpu().numpy(), dx) < 1e-5
+    # fused act' of the producing layer: x plays the role of that layer's stored output
+    C.call('tn_conv2d_dgrad', C.ptr(gzd), C.ptr(Wd), C.ptr(dxd), C.ptr(xd), B, Cin, S, M, f, pad_lo,
+           out_sz, *C.act_code('relu07'), None)
+    sync()
+    want = O.act_backward('relu07', x, x, dx)      # sign(a) == sign(z) for leaky relu
+    assert rel(dxd.cpu().numpy(), want) < 1e-5
+    nb = C.lib.tn_conv2d_wgrad_workspace_bytes(B, Cin, S, M, f)
+    ws = torch.zeros(nb // 4 + 1, device='cuda')
+    dWd, dbd = torch.zeros_like(Wd), torch.zeros_like(bd)
+    C.call('tn_conv2d_wgrad', C.ptr(xd), C.ptr(gzd), C.ptr(dWd), C.ptr(dbd), C.ptr(ws), B, Cin, S,
+           M, f, pad_lo, out_sz, None)
+    sync()
+    assert rel(dWd.cpu().numpy(), dW) < 1e-5
+    assert rel(dbd.cpu().numpy(), db) < 1e-5
+
+
+def test_conv_wgrad_many_images_is_deterministic(C):
+    B, Cin, S, M, f = 700, 4, 13, 20, 3          # more images than CTAs: grid-stride + 2 stages
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((B, Cin, S, S)).astype(np.float32)
+    gz = rng.standard_normal((B, M, 11, 11)).astype(np.float32)
+    W = np.zeros((M, Cin, f, f), np.float32)
+    _, cache = O.conv_forward(x.astype(np.float64), W.astype(np.float64), 'valid')
+    dW, db, _ = O.conv_backward(gz.astype(np.float64), W.astype(np.float64), cache, need_dx=False)
+    nb = C.lib.tn_conv2d_wgrad_workspace_bytes(B, Cin, S, M, f)
+    ws = torch.zeros(nb // 4 + 1, device='cuda')
+    xd, gzd = dev(x), dev(gz)
+    res = []
+    for _ in range(2):
+        dWd, dbd = torch.zeros((M, Cin, f, f), device='cuda'), torch.zeros(M, device='cuda')
+        C.call('tn_conv2d_wgrad', C.ptr(xd), C.ptr(gzd), C.ptr(dWd), C.ptr(dbd), C.ptr(ws), B, Cin,
+               S, M, f, 0, 11, None)
+        sync()
+        res.append((dWd.cpu().numpy(), dbd.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert rel(res[0][0], dW) < 1e-4 and rel(res[0][1], db) < 1e-4
+
+
+def test_conv_direct_path_refuses_oversized_shapes(C):
+    x = torch.zeros((1, 64, 32, 32), device='cuda')
+    W = torch.zeros((128, 64, 3, 3), device='cuda')
+    ws = torch.zeros(16, device='cuda')
+    rc = C.lib.tn_conv2d_wgrad(C.ptr(x), C.ptr(x), C.ptr(W), C.ptr(W), C.ptr(ws), 1, 64, 32, 128, 3,
+                               1, 32, None)
+    assert rc == -5 and 'implicit-GEMM' in C.last_error()
+
+
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('S,p,ib', [(26, 2, False), (11, 2, False), (11, 2, True), (7, 3, False),
+                                    (62, 2, False), (9, 4, True), (5, 5, False)])
+def test_pool_fwd_bwd_bit_exact_with_ties(C, S, p, ib):
+    rng = np.random.default_rng(S * 10 + p)
+    B, C_ = 3, 4
+    x = rng.integers(-3, 3, size=(B, C_, S, S)).astype(np.float32)         # many ties
+    x[0, 0] = -5.0                                                         # all-negative, all-tied
+    out, cache = O.pool_forward(x, p, ib)
+    o = O.pool_out_size(S, p, ib)
+    xd = dev(x)
+    outd = torch.zeros((B, C_, o, o), device='cuda')
+    C.call('tn_maxpool_fwd', C.ptr(xd), C.ptr(outd), B * C_, S, p, o, None)
+    sync()
+    assert np.array_equal(outd.cpu().numpy(), out)
+    dout = rng.standard_normal(out.shape).astype(np.float32)
+    dx = O.pool_backward(dout, cache)
+    dxd = torch.zeros_like(xd)
+    C.call('tn_maxpool_bwd', C.ptr(dev(dout)), C.ptr(xd), C.ptr(outd), C.ptr(dxd), B * C_, S, p, o,
+           0, 0, None)
+    sync()
+    assert np.array_equal(dxd.cpu().numpy(), dx)
+    # fused activation derivative (leaky relu, slope from the sign of the stored output)
+    C.call('tn_maxpool_bwd', C.ptr(dev(dout)), C.ptr(xd), C.ptr(outd), C.ptr(dxd), B * C_, S, p, o,
+           *C.act_code('relu10'), None)
+    sync()
+    want = O.act_backward('relu10', x, x, dx)
+    assert np.array_equal(dxd.cpu().numpy(), want)
+
+
+# --------------------------------------------------------------------------------------------
+DENSE_CASES = [(20, 720, 500, 'relu01', .5), (128, 784, 1000, 'relu10', .5), (33, 500, 10, 'linear', 0),
+               (17, 1000, 457, 'linear', 0), (64, 100, 36, 'tanh', .25), (5, 7, 3, 'sigmoid', 0)]
+
+
+@pytest.mark.parametrize('case', range(len(DENSE_CASES)))
+def test_dense_fwd_bwd(C, case):
+    B, n_in, n_out, actn, pdrop = DENSE_CASES[case]
+    rng = np.random.default_rng(300 + case)
+    x = rng.standard_normal((B, n_in)).astype(np.float32)
+    W = (rng.standard_normal((n_in, n_out)) / np.sqrt(n_in)).astype(np.float32)
+    b = rng.standard_normal(n_out).astype(np.float32)
+    seed, step, s0 = 802165, 11, 256
+    ctl = make_ctl(C, step=step, sample0=s0)
+    act, nn = C.act_code(actn)
+    a = O.act_forward(actn, x @ W + b)
+    mask = philox.bernoulli_mask(seed, philox.PURPOSE_DROPOUT, step, np.arange(s0, s0 + B), n_out,
+                                 1 - pdrop) if pdrop else np.ones_like(a)
+    xd, Wd, bd = dev(x), dev(W), dev(b)
+    out = torch.zeros((B, n_out), device='cuda')
+    C.call('tn_dense_fwd', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(out), B, n_in, n_out, act, nn,
+           1. - pdrop, seed, C.ptr(ctl), None, 1.0, None)
+    sync()
+    got = out.cpu().numpy()
+    assert np.array_equal(got == 0, (a * mask) == 0) or pdrop == 0      # same mask pattern
+    assert rel(got, a * mask) < 1e-5
+    # test twin: no mask, scaled by (1 - pdrop)
+    C.call('tn_dense_fwd', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(out), B, n_in, n_out, act, nn,
+           1.0, 0, C.ptr(ctl), None, float(1 - pdrop), None)
+    sync()
+    assert rel(out.cpu().numpy(), a * np.float32(1 - pdrop)) < 1e-5
+    # injected mask
+    mi = (rng.uniform(0, 1, a.shape) < .7).astype(np.float32)
+    C.call('tn_dense_fwd', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(out), B, n_in, n_out, act, nn,
+           1.0, 0, C.ptr(ctl), C.ptr(dev(mi)), 1.0, None)
+    sync()
+    assert rel(out.cpu().numpy(), a * mi) < 1e-5
+    # backward
+    g = rng.standard_normal((B, n_out)).astype(np.float32)
+    gd = dev(g)
+    dW, db = torch.zeros_like(Wd), torch.zeros_like(bd)
+    C.call('tn_dense_bwd_weights', C.ptr(xd), C.ptr(gd), C.ptr(dW), C.ptr(db), B, n_in, n_out, None)
+    sync()
+    assert rel(dW.cpu().numpy(), x.T @ g) < 1e-5
+    assert rel(db.cpu().numpy(), g.sum(0)) < 1e-5
+    dx = torch.zeros_like(xd)
+    C.call('tn_dense_bwd_data', C.ptr(gd), C.ptr(Wd), C.ptr(dx), B, n_in, n_out, None, 0, 0, 1.0,
+           0, C.ptr(ctl), None, None)
+    sync()
+    assert rel(dx.cpu().numpy(), g @ W.T) < 1e-5
+    # fused: previous dense layer with dropout + leaky relu; prev_out = its stored masked output
+    pm = philox.bernoulli_mask(77, philox.PURPOSE_DROPOUT, step, np.arange(s0, s0 + B), n_in, .5)
+    prev_a = O.act_forward('relu01', x)
+    prev_out = (prev_a * pm).astype(np.float32)
+    C.call('tn_dense_bwd_data', C.ptr(gd), C.ptr(Wd), C.ptr(dx), B, n_in, n_out, C.ptr(dev(prev_out)),
+           *C.act_code('relu01'), .5, 77, C.ptr(ctl), None, None)
+    sync()
+    want = O.act_backward('relu01', x, prev_a, (g @ W.T) * pm)
+    assert rel(dx.cpu().numpy(), want) < 1e-5
+
+
+def test_dropout_apply_and_act_bwd(C):
+    rng = np.random.default_rng(9)
+    B, n = 9, 1001
+    x = rng.standard_normal((B, n)).astype(np.float32)
+    seed, step, s0 = 5, 2, 10
+    ctl = make_ctl(C, step=step, sample0=s0)
+    out = torch.zeros((B, n), device='cuda')
+    C.call('tn_dropout_apply', C.ptr(dev(x)), C.ptr(out), B, n, .8, seed, C.ptr(ctl), None, 1.0, None)
+    sync()
+    m = philox.bernoulli_mask(seed, philox.PURPOSE_DROPOUT, step, np.arange(s0, s0 + B), n, .8)
+    assert np.array_equal(out.cpu().numpy(), x * m)
+    C.call('tn_dropout_apply', C.ptr(dev(x)), C.ptr(out), B, n, 1.0, 0, C.ptr(ctl), None, 0.8, None)
+    sync()
+    assert np.array_equal(out.cpu().numpy(), x * np.float32(.8))
+    for actn in ['relu05', 'tanh', 'sigmoid', 'scaled_tanh', 'softplus', 'relu', 'linear']:
+        z = rng.standard_normal((B, n)).astype(np.float32)
+        a = O.act_forward(actn, z)
+        g = rng.standard_normal((B, n)).astype(np.float32)
+        gz = torch.zeros((B, n), device='cuda')
+        C.call('tn_act_bwd', C.ptr(dev(g)), C.ptr(dev(a)), C.ptr(gz), B * n, *C.act_code(actn), None)
+        sync()
+        assert rel(gz.cpu().numpy(), O.act_backward(actn, z, a, g)) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('B,n', [(20, 10), (128, 457), (7, 3), (1024, 10)])
+def test_softmax_nll_and_test_stats(C, B, n):
+    rng = np.random.default_rng(B + n)
+    z = (3 * rng.standard_normal((B, n))).astype(np.float32)
+    z[0, :] = 1.5                                   # full tie: argmax must be the first index
+    ycorp = rng.integers(0, n, B + 5).astype(np.int32)
+    ycorp[5], ycorp[6] = 0, n - 1
+    row0 = 5
+    ctl = make_ctl(C, row0=row0)
+    y = ycorp[row0:row0 + B]
+    lp = O.log_softmax(z)
+    g = np.exp(lp)
+    g[np.arange(B), y] -= 1
+    g /= np.float32(2 * B)
+    zd, yd = dev(z), dev(ycorp)
+    lpd, gd = torch.zeros((B, n), device='cuda'), torch.zeros((B, n), device='cuda')
+    rl = torch.zeros(B, device='cuda')
+    C.call('tn_softmax_nll_fwd_bwd', C.ptr(zd), C.ptr(yd), None, C.ptr(ctl), B, n, 1. / (2 * B),
+           C.ptr(lpd), C.ptr(gd), C.ptr(rl), None)
+    nll = torch.zeros(1, device='cuda')
+    C.call('tn_reduce_rowloss', C.ptr(rl), B, C.ptr(nll), None)
+    sync()
+    assert rel(lpd.cpu().numpy(), lp) < 1e-5
+    assert rel(gd.cpu().numpy(), g) < 1e-5
+    assert rel(rl.cpu().numpy(), -lp[np.arange(B), y]) < 1e-5
+    assert abs(nll.item() - (-lp[np.arange(B), y]).sum()) < 1e-4 * B
+    preds = torch.zeros(B, dtype=torch.int64, device='cuda')
+    stats = torch.zeros(2 + 2 * B, device='cuda')
+    idx = np.arange(row0, row0 + B).astype(np.int32)            # same rows through the index path
+    C.call('tn_softmax_test_stats', C.ptr(zd), C.ptr(yd), C.ptr(dev(idx)), None, B, n, C.ptr(lpd),
+           C.ptr(preds), C.ptr(stats), None)
+    sync()
+    want_pred = np.argmax(z, axis=1)
+    assert np.array_equal(preds.cpu().numpy(), want_pred)
+    st = stats.cpu().numpy()
+    assert abs(st[0] - np.mean(want_pred != y)) < 1e-6
+    assert abs(st[1] - np.mean(np.exp(lp)[np.arange(B), y])) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------
+def test_update_all_ranks_l1_l2_frozen(C):
+    rng = np.random.default_rng(11)
+    shapes = [((20, 4, 3, 3), dict(maxnorm=.9)), ((20,), dict(maxnorm=.05)),
+              ((37, 50), dict(maxnorm=1.1, L2=.001)), ((50,), dict(L1=.01)),
+              ((50, 11), dict(rate=0, L2=.1)), ((11,), dict(rate=.5, momentum=.8)),
+              ((6, 4), dict(maxnorm=2.))]
+    offs, total = [], 0
+    for shp, _ in shapes:
+        offs.append(total)
+        total += (int(np.prod(shp)) + 3) // 4 * 4
+    theta, vel, grad = [rng.standard_normal(total).astype(np.float32) for _ in range(3)]
+    vel *= 5
+    segs = (C.ParamSeg * len(shapes))()
+    lr = np.float32(.1)
+    want_t, want_v = theta.copy(), vel.copy()
+    wtcost = 0.
+    for i, (shp, r) in enumerate(shapes):
+        reg = dict(O.DEFAULT_REG, **r)
+        n = int(np.prod(shp))
+        o = offs[i]
+        th = theta[o:o + n].reshape(shp).copy()
+        if shp == (6, 4):
+            th[:, 1] = 0                       # zero-norm column: scale must be exactly 1
+            theta[o:o + n] = th.ravel()
+            vel[o:o + n].reshape(shp)[:, 1] = 0
+            want_t[o:o + n] = th.ravel()
+            want_v[o:o + n] = vel[o:o + n]
+        if shp == (50,):
+            th[:5] = 0                         # L1 at theta == 0 contributes sgn = 0
+            theta[o:o + n] = th.ravel()
+            want_t[o:o + n] = th.ravel()
+        s = segs[i]
+        s.offset, s.size, s.ndim = o, n, len(shp)
+        s.rows, s.cols = (shp[0], n // shp[0]) if len(shp) > 1 else (1, n)
+        s.momentum, s.rate, s.maxnorm = reg['momentum'], reg['rate'], reg['maxnorm']
+        s.l1, s.l2 = reg['L1'], reg['L2']
+        wtcost += reg['L1'] * np.abs(th).sum() + reg['L2'] * (th * th).sum()
+        if reg['rate']:
+            gk = grad[o:o + n].reshape(shp)
+            if reg['L1']:
+                gk = gk + np.float32(reg['L1']) * np.sign(th)
+            if reg['L2']:
+                gk = gk + np.float32(2 * reg['L2']) * th
+            t2, v2 = O.sgd_update(th, vel[o:o + n].reshape(shp), gk, reg, lr)
+            want_t[o:o + n], want_v[o:o + n] = t2.ravel(), v2.ravel()
+    td, vd, gd = dev(theta), dev(vel), dev(grad)
+    nb = C.lib.tn_update_workspace_bytes(len(shapes), total)
+    ws = torch.zeros(nb // 4 + 1, device='cuda')
+    nll = dev(np.array([12.5], np.float32))
+    cost = torch.zeros(1, device='cuda')
+    C.call('tn_sgd_momentum_maxnorm_update', C.ptr(td), C.ptr(vd), C.ptr(gd), segs, len(shapes),
+           total, C.ptr(make_ctl(C, lr=lr)), 1.0, C.ptr(nll), 0.25, C.ptr(cost), C.ptr(ws), None)
+    sync()
+    assert rel(td.cpu().numpy(), want_t) < 1e-6
+    assert rel(vd.cpu().numpy(), want_v) < 1e-6
+    assert abs(cost.item() - (12.5 * .25 + wtcost)) < 1e-4 * (1 + abs(wtcost))
+    # frozen segment untouched, bit for bit
+    o = offs[4]
+    assert np.array_equal(td.cpu().numpy()[o:o + 550], theta[o:o + 550])
+    assert np.array_equal(vd.cpu().numpy()[o:o + 550], vel[o:o + 550])

@@ -1,0 +1,233 @@
+"""Whole-step parity: NeuralNet (CUDA kernels through the C ABI) against the CPU oracle over many
+training steps on the same seeded data, with the SAME Philox streams on both sides (the oracle
+regenerates the device's dropout masks, flip noise and elastic field bit for bit).
+
+Tolerance (north_star): max|a-b| / max|b| <= 1e-3 per tensor in float32; the first step must leave
+every parameter bit-identical (lagged momentum).
+
+The synthetic images here are dense (no exactly-equal neighbouring pixels): max-pool ties route
+the gradient to every tied element, so on flat regions a last-ulp difference in a conv sum
+between two correct implementations changes which elements are "tied" -- the per-kernel tests
+cover tie routing bit-exactly on identical inputs instead."""
+import ast
+import copy
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import theanet_oracle as O
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-3
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def load_prms(name, B, img_sz, seed=555555):
+    with open(os.path.join(ROOT, 'params', name)) as f:
+        p = ast.literal_eval(f.read())
+    p['training_params']['SEED'] = seed
+    p['training_params']['BATCH_SZ'] = B
+    p['layers'][0][1]['img_sz'] = img_sz
+    return p
+
+
+def synth(n, c, s, n_classes, seed=1234, dense=True):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (n, c, s, s)).astype(np.float32)
+    if not dense:
+        x = x * (x > .8)
+    y = rng.integers(0, n_classes, n).astype(np.int32)
+    return x, y
+
+
+SMALL_NET = {
+    "layers": [
+        ('ElasticLayer', {'num_maps': 3, 'translation': 1.5, 'zoom': 1.2, 'magnitude': 12,
+                          'sigma': 3, 'pflip': 0.02, 'angle': 10, 'nearest': False,
+                          'invert_image': False}),
+        ('ConvLayer', {'num_maps': 8, 'filter_sz': 3, 'stride': 1, 'mode': 'same',
+                       'actvn': 'relu05', 'reg': {'maxnorm': .8}}),
+        ('ConvLayer', {'num_maps': 6, 'filter_sz': 5, 'stride': 1, 'mode': 'valid',
+                       'actvn': 'tanh', 'reg': {'L1': 1e-4, 'momentum': .9}}),
+        ('PoolLayer', {'pool_sz': 3}),
+        ('DropOutLayer', {'pdrop': .2}),
+        ('HiddenLayer', {'n_out': 64, 'pdrop': .3, 'actvn': 'relu10',
+                         'reg': {'maxnorm': 1.5, 'L1': 1e-4}}),
+        ('DropOutLayer', {'pdrop': .1}),
+        ('HiddenLayer', {'n_out': 33, 'actvn': 'scaled_tanh', 'reg': {'rate': .5}}),
+        ('SoftmaxLayer', {'n_out': 11, 'reg': {'L2': 1e-3, 'maxnorm': 2.}}),
+    ],
+    "training_params": {'BATCH_SZ': 16, 'NUM_EPOCHS': 1, 'EPOCHS_TO_TEST': 1, 'TEST_SAMP_SZ': 16,
+                        'INIT_LEARNING_RATE': .2, 'EPOCHS_TO_HALF_RATE': 2, 'SEED': 4242},
+}
+
+
+def compare_nets(net, on, tag):
+    for li, (a, b) in enumerate(zip(net.get_init_params()['allwts'], on.get_wts())):
+        for k, (u, v) in enumerate(zip(a, b)):
+            assert rel(u, v) < TOL, '{} layer {} tensor {}: {}'.format(tag, li, k, rel(u, v))
+    for li, (vs, L) in enumerate(zip(net.get_velocities(), on.spec)):
+        for k, u in enumerate(vs):
+            r = rel(u, L['vel'][k])
+            assert r < TOL or np.max(np.abs(L['vel'][k])) < 1e-12, \
+                '{} velocity layer {} tensor {}: {}'.format(tag, li, k, r)
+
+
+def run_pair(prms, x, y, steps, use_graph, check_at=(1, 2, 5), **trin_kw):
+    from theanet_b200.neuralnet import NeuralNet
+    p_dev, p_cpu = copy.deepcopy(prms), copy.deepcopy(prms)
+    net = NeuralNet(p_dev['layers'], p_dev['training_params'], use_graph=use_graph)
+    on = O.OracleNet(p_cpu['layers'], p_cpu['training_params'])
+    B = prms['training_params']['BATCH_SZ']
+    fn = net.get_trin_model(x, y, **trin_kw)
+    init = net.get_init_params()['allwts']
+    nb = len(x) // B
+    costs = []
+    for s in range(steps):
+        i = s % nb
+        cost, feats, lp = fn(i)
+        ocost, olp = on.train_step(x[i * B:(i + 1) * B], y[i * B:(i + 1) * B], step=s, sample0=0)
+        assert abs(cost - ocost) <= TOL * abs(ocost), 'step {} cost {} vs {}'.format(s, cost, ocost)
+        assert rel(lp, olp) < TOL, 'step {} logprob {}'.format(s, rel(lp, olp))
+        assert feats is lp or np.array_equal(feats, lp)
+        costs.append((float(cost), float(ocost)))
+        if s == 0:      # lagged momentum: nothing moves on the first step
+            for a, b in zip(init, net.get_init_params()['allwts']):
+                for u, v in zip(a, b):
+                    assert np.array_equal(u, v)
+        if s + 1 in check_at or s + 1 == steps:
+            compare_nets(net, on, 'after step {}'.format(s + 1))
+        if (s + 1) % nb == 0:
+            net.inc_epoch_set_rate()
+            on.inc_epoch_set_rate()
+    return net, on, costs
+
+
+@pytest.mark.parametrize('B,use_graph', [(20, False), (128, True)])
+def test_mnist_prms_training_matches_oracle(B, use_graph):
+    prms = load_prms('mnist.prms', B, 28)
+    x, y = synth(B * 4, 1, 28, 10)
+    run_pair(prms, x, y, 10, use_graph)
+
+
+def test_mnist_prms_100_steps_curve():
+    prms = load_prms('mnist.prms', 20, 28)
+    x, y = synth(20 * 10, 1, 28, 10)
+    _, _, costs = run_pair(prms, x, y, 100, True, check_at=(1, 2, 10, 100))
+    c = np.array(costs)
+    assert np.max(np.abs(c[:, 0] - c[:, 1]) / np.abs(c[:, 1])) < TOL
+
+
+def test_3flat_prms_training_matches_oracle():
+    prms = load_prms('3flat.prms', 20, 28)
+    x, y = synth(20 * 3, 1, 28, 457)
+    run_pair(prms, x, y, 8, True)
+
+
+def test_small_net_all_layer_kinds_bilinear_maxnorm_l1():
+    prms = copy.deepcopy(SMALL_NET)
+    prms['layers'][0][1]['img_sz'] = 17
+    x, y = synth(16 * 3, 3, 17, 11)
+    run_pair(prms, x, y, 12, False)
+    run_pair(prms, x, y, 12, True)
+
+
+def test_graph_and_eager_are_bit_identical_and_host_streaming_matches():
+    prms = load_prms('mnist.prms', 32, 28)
+    x, y = synth(32 * 3, 1, 28, 10)
+    outs = []
+    for kw in (dict(use_graph=False), dict(use_graph=True), dict(use_graph=True, resident=False)):
+        from theanet_b200.neuralnet import NeuralNet
+        p = copy.deepcopy(prms)
+        net = NeuralNet(p['layers'], p['training_params'], use_graph=kw.pop('use_graph'))
+        fn = net.get_trin_model(x, y, **kw)
+        res = [fn(i % 3) for i in range(7)]
+        outs.append((res, net.get_init_params()['allwts']))
+    for other in outs[1:]:
+        for (c0, f0, _), (c1, f1, _) in zip(outs[0][0], other[0]):
+            assert c0 == c1 and np.array_equal(f0, f1)
+        for a, b in zip(outs[0][1], other[1]):
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+
+
+def test_index_list_mode_matches_slices():
+    from theanet_b200.neuralnet import NeuralNet
+    prms = load_prms('mnist.prms', 16, 28)
+    x, y = synth(64, 1, 28, 10)
+    perm = np.random.default_rng(3).permutation(64).astype(np.int32)
+    p1, p2 = copy.deepcopy(prms), copy.deepcopy(prms)
+    n1 = NeuralNet(p1['layers'], p1['training_params'])
+    n2 = NeuralNet(p2['layers'], p2['training_params'])
+    f1 = n1.get_trin_model(x, y, take_index_list=True)
+    f2 = n2.get_trin_model(x[perm], y[perm])
+    for i in range(4):
+        c1, l1, _ = f1(perm[i * 16:(i + 1) * 16])
+        c2, l2, _ = f2(i)
+        assert c1 == c2 and np.array_equal(l1, l2)
+
+
+def test_test_twin_and_checkpoint_roundtrip(tmp_path):
+    from theanet_b200.neuralnet import NeuralNet
+    prms = load_prms('mnist.prms', 25, 28)
+    x, y = synth(100, 1, 28, 10, dense=False)          # MNIST-like sparse images are fine forward
+    p_dev, p_cpu = copy.deepcopy(prms), copy.deepcopy(prms)
+    net = NeuralNet(p_dev['layers'], p_dev['training_params'])
+    on = O.OracleNet(p_cpu['layers'], p_cpu['training_params'])
+    te = net.get_test_model(x, y, preds_feats=True)
+    for i in range(4):
+        err, pmle, feats, preds = te(i)
+        oerr, opmle, olp, opreds = on.test_step(x[i * 25:(i + 1) * 25], y[i * 25:(i + 1) * 25])
+        assert rel(feats, olp) < TOL
+        assert np.array_equal(preds, opreds) and preds.dtype == np.int64
+        assert abs(err - oerr) < 1e-6 and abs(pmle - opmle) < TOL * abs(opmle)
+    # train a little, checkpoint through pickle (the reference's .pkl schema), reload, same outputs
+    tr = net.get_trin_model(x, y)
+    for i in range(4):
+        tr(i)
+    pkl = tmp_path / 'net.pkl'
+    with open(pkl, 'wb') as f:
+        pickle.dump(net.get_init_params(), f, -1)
+    with open(pkl, 'rb') as f:
+        saved = pickle.load(f)
+    assert [len(w) for w in saved['allwts']] == [0, 2, 0, 2, 0, 2, 2]
+    assert saved['allwts'][1][0].shape == (4, 1, 3, 3) and saved['allwts'][5][0].shape == (720, 500)
+    net2 = NeuralNet(saved['layers'], saved['training_params'], saved['allwts'])
+    te2 = net2.get_test_model(x, y, preds_feats=True)
+    a, b = te(1), te2(1)
+    assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+    dt = net2.get_data_test_model(get_output_of_layers=(2,))
+    feats, preds, pooled = dt(x[25:50])
+    assert np.array_equal(feats, b[2]) and np.array_equal(preds, b[3])
+    assert pooled.shape == (25, 4, 13, 13)
+
+
+def test_elastic_debugout_matches_oracle_field():
+    from theanet_b200.neuralnet import NeuralNet
+    from oracle import philox
+    prms = load_prms('mnist.prms', 8, 28)
+    x, y = synth(16, 1, 28, 10)
+    net = NeuralNet(prms['layers'], prms['training_params'], use_graph=False)
+    net.debug_elastic = True
+    fn = net.get_trin_model(x, y)
+    fn(0)
+    fn(1)
+    seed = net.tr_layers[0].seed
+    noise = philox.elastic_noise(seed, 1, 2 * 28 * 28).reshape(2, 28, 28)
+    u = philox.elastic_scalars(seed, 1)
+    ty, tx, disp = O.elastic_target(28, prms['layers'][0][1], noise, u)
+    got_disp, got_tyx = net.elastic_debugout()
+    assert np.max(np.abs(got_disp - disp)) < 1e-4        # noise may differ in the last float32 ulp
+    assert np.max(np.abs(got_tyx[0] - ty)) < 1e-4
+    # the output of the layer is the oracle's warp of the same batch, bit for bit
+    fm = philox.bernoulli_mask(seed, philox.PURPOSE_FLIP, 1, np.arange(8), 784, .03).reshape(8, 1, 28, 28)
+    want = O.elastic_apply(x[8:16], prms['layers'][0][1], ty, tx, fm)
+    assert np.mean(net.out[0].cpu().numpy() == want) > 0.999

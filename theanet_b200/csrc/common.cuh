@@ -1,0 +1,126 @@
+// Shared device helpers: error plumbing, activations (theanet/layer/layer.py:27-39) and the
+// Philox4x32-10 streams (CPU twin: oracle/philox.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/theanet_b200.h"
+
+namespace tn {
+
+void set_error(const char *fmt, ...);
+
+#define TN_REQUIRE(cond, code, ...)      \
+  do {                                   \
+    if (!(cond)) {                       \
+      tn::set_error(__VA_ARGS__);        \
+      return (code);                     \
+    }                                    \
+  } while (0)
+
+#define TN_LAUNCH_CHECK(name)                                                     \
+  do {                                                                            \
+    cudaError_t e__ = cudaGetLastError();                                         \
+    if (e__ != cudaSuccess) {                                                     \
+      tn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
+      return TN_ERR_CUDA;                                                         \
+    }                                                                             \
+  } while (0)
+
+constexpr int kNumSM = 148;
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+__host__ __device__ inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------
+// Activations.  Forward follows layer.py:36 literally (max(0,x) + (min(0,x)*NN)/100, each op
+// rounded in float32) so reluNN is bit-exact against the numpy restatement.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_fwd(float z, int act, float nn) {
+  switch (act) {
+    case TN_ACT_LINEAR: return z;
+    case TN_ACT_RELU: return fmaxf(0.f, z);
+    case TN_ACT_LEAKY: return z > 0.f ? z : __fdiv_rn(__fmul_rn(fminf(0.f, z), nn), 100.f);
+    case TN_ACT_TANH: return tanhf(z);
+    case TN_ACT_SCALED_TANH: return 1.7f * tanhf(__fdiv_rn(2.f * z, 3.f));
+    case TN_ACT_SIGMOID: return __fdiv_rn(1.f, 1.f + expf(-z));
+    case TN_ACT_SOFTPLUS: return z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
+  }
+  return z;
+}
+
+// d act / dz expressed through the stored output a = act(z).  For reluNN (NN >= 1) sign(a) ==
+// sign(z), and at exactly 0 Theano's maximum/minimum gradients both fire (slope 1 + NN/100).
+// For relu / relu00 a == 0 stands for every z <= 0 and gets slope 0 (z == 0 exactly is the only
+// deviation from Theano, a measure-zero event).
+__device__ __forceinline__ float act_bwd_from_out(float a, int act, float nn) {
+  switch (act) {
+    case TN_ACT_LINEAR: return 1.f;
+    case TN_ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case TN_ACT_LEAKY: {
+      if (nn == 0.f) return a > 0.f ? 1.f : 0.f;
+      const float s = __fdiv_rn(nn, 100.f);
+      return a > 0.f ? 1.f : (a < 0.f ? s : 1.f + s);
+    }
+    case TN_ACT_TANH: return 1.f - a * a;
+    case TN_ACT_SCALED_TANH: {
+      const float t = __fdiv_rn(a, 1.7f);
+      return (1.7f * 2.f / 3.f) * (1.f - t * t);
+    }
+    case TN_ACT_SIGMOID: return a * (1.f - a);
+    case TN_ACT_SOFTPLUS: return 1.f - expf(-a);
+  }
+  return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10.  key = (seed lo, seed hi); ctr = (block, sample, step, purpose); element j of a
+// sample is word j%4 of block j/4.
+// ------------------------------------------------------------------------------------------------
+struct Philox4 {
+  uint32_t x, y, z, w;
+};
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                          uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c1 ^ k0;
+    const uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+__host__ __device__ __forceinline__ Philox4 philox_block(uint64_t seed, int purpose, uint32_t step,
+                                                         uint32_t sample, uint32_t block) {
+  return philox4x32_10(block, sample, step, (uint32_t)purpose, (uint32_t)(seed & 0xffffffffu),
+                       (uint32_t)(seed >> 32));
+}
+
+__device__ __forceinline__ uint32_t philox_word(const Philox4 &p, int k) {
+  return k == 0 ? p.x : (k == 1 ? p.y : (k == 2 ? p.z : p.w));
+}
+
+// uint32 threshold t with P(word < t) ~ p (oracle/philox.py bernoulli_threshold); p >= 1 is the
+// caller's business.
+inline uint32_t bernoulli_threshold(double p) {
+  double t = floor(p * 4294967296.0);
+  if (t < 0) t = 0;
+  if (t > 4294967295.0) t = 4294967295.0;
+  return (uint32_t)t;
+}
+
+__device__ __forceinline__ float ctl_lr(const int32_t *ctl) {
+  return __int_as_float(ctl[TN_CTL_LR_BITS]);
+}
+
+}  // namespace tn

@@ -1,0 +1,198 @@
+// Layer.get_updates / get_wtcost (theanet/layer/layer.py:70-117) for ALL parameter tensors in one
+// pass over the flat theta / velocity / gradient buffers:
+//     g'     = g*grad_scale + L1*sgn(theta) + 2*L2*theta
+//     v'     = m*v + (1-m)*g'
+//     theta' = theta - rate*lr*v          <- the OLD velocity (Theano updates are simultaneous)
+//     maxnorm: 1-D clip; 2-D per-column (axis 0) norm; 4-D per-output-kernel norm
+//     cost   = nll + sum_layers L1*sum|theta| + L2*sum theta^2   (pre-update theta)
+// Pure HBM work: 3 reads + 2 writes of 4 B per parameter.
+#include "common.cuh"
+
+namespace tn {
+
+constexpr int kMaxSegs = 64;
+constexpr int kUpdThreads = 256;
+constexpr int kUpdPerBlock = kUpdThreads * 4;
+
+struct SegTable {
+  tn_param_seg seg[kMaxSegs];
+  int first_block[kMaxSegs + 1];
+  int nseg;
+};
+
+__global__ void __launch_bounds__(kUpdThreads)
+sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float *__restrict__ grad,
+                const __grid_constant__ SegTable tab, const int32_t *__restrict__ ctl,
+                float grad_scale, float *__restrict__ wt_partial) {
+  __shared__ float red[kUpdThreads / 32];
+  int s = 0;
+  while (s + 1 < tab.nseg && (int)blockIdx.x >= tab.first_block[s + 1]) ++s;
+  const tn_param_seg &sg = tab.seg[s];
+  const int64_t base = sg.offset + (int64_t)(blockIdx.x - tab.first_block[s]) * kUpdPerBlock;
+  const int64_t end = sg.offset + sg.size;
+  const float lr = ctl_lr(ctl);
+  const float step = __fmul_rn(sg.rate, lr);
+  const float m = sg.momentum, om = __fsub_rn(1.f, m);
+  const float l2x2 = 2.f * sg.l2;
+  const bool clip1d = sg.ndim == 1 && sg.maxnorm != 0.f;
+  float wsum = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int64_t i = base + q * kUpdThreads + threadIdx.x;
+    if (i < end) {
+      const float th = theta[i];
+      if (sg.l1 != 0.f) wsum = fmaf(sg.l1, fabsf(th), wsum);
+      if (sg.l2 != 0.f) wsum = fmaf(sg.l2, th * th, wsum);
+      if (sg.rate != 0.f) {
+        float g = grad_scale == 1.f ? grad[i] : __fmul_rn(grad[i], grad_scale);
+        if (sg.l1 != 0.f) {
+          const float sgn = th > 0.f ? 1.f : (th < 0.f ? -1.f : 0.f);
+          g = __fadd_rn(g, __fmul_rn(sg.l1, sgn));
+        }
+        if (sg.l2 != 0.f) g = __fadd_rn(g, __fmul_rn(l2x2, th));
+        const float v = vel[i];
+        vel[i] = __fadd_rn(__fmul_rn(m, v), __fmul_rn(om, g));
+        float tn_ = __fsub_rn(th, __fmul_rn(step, v));
+        if (clip1d) tn_ = fminf(fmaxf(tn_, -sg.maxnorm), sg.maxnorm);
+        theta[i] = tn_;
+      }
+    }
+  }
+  // block partial of the weight cost (fixed-order shuffle tree)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = wsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kUpdThreads / 32; ++w) t += red[w];
+    wt_partial[blockIdx.x] = t;
+  }
+}
+
+__device__ __forceinline__ float maxnorm_scale(float sumsq, float maxnorm) {
+  const float n = sqrtf(sumsq);
+  const float d = fminf(fmaxf(n, 0.f), maxnorm);
+  return __fdiv_rn(__fadd_rn(1e-7f, d), __fadd_rn(1e-7f, n));
+}
+
+// 2-D (rows x cols): per-column norm over axis 0; 32 columns x 8 row-slices per CTA
+__global__ void maxnorm_cols_kernel(float *__restrict__ w, int rows, int cols, float maxnorm) {
+  __shared__ float red[8][33];
+  __shared__ float scale[32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = ty; r < rows; r += 8) {
+      const float v = w[(size_t)r * cols + c];
+      s = fmaf(v, v, s);
+    }
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0) {
+    float t = red[0][tx];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) t += red[q][tx];
+    scale[tx] = maxnorm_scale(t, maxnorm);
+  }
+  __syncthreads();
+  if (c < cols) {
+    const float sc = scale[tx];
+    if (sc != 1.f)
+      for (int r = ty; r < rows; r += 8) w[(size_t)r * cols + c] *= sc;
+  }
+}
+
+// 4-D (rows = output kernels, cols = C*f*f contiguous): one warp per row
+__global__ void maxnorm_rows_kernel(float *__restrict__ w, int rows, int cols, float maxnorm) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float *row = w + (size_t)r * cols;
+  float s = 0.f;
+  for (int j = lane; j < cols; j += 32) s = fmaf(row[j], row[j], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float sc = maxnorm_scale(s, maxnorm);
+  if (sc != 1.f)
+    for (int j = lane; j < cols; j += 32) row[j] *= sc;
+}
+
+__global__ void finish_cost_kernel(const float *__restrict__ wt_partial, int n,
+                                   const float *__restrict__ nll_sum, float nll_scale,
+                                   float *__restrict__ cost_out) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) s += wt_partial[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cost_out[0] = (nll_sum ? nll_sum[0] * nll_scale : 0.f) + red[0];
+}
+
+static int64_t update_blocks(const tn_param_seg *segs, int nseg, int *first_block) {
+  int64_t nb = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (first_block) first_block[s] = (int)nb;
+    nb += ceil_div64(segs[s].size, kUpdPerBlock);
+  }
+  if (first_block) first_block[nseg] = (int)nb;
+  return nb;
+}
+
+}  // namespace tn
+
+using namespace tn;
+
+extern "C" size_t tn_update_workspace_bytes(int nseg, int64_t total) {
+  // one float per CTA of the step kernel; bounded by total/1024 + nseg
+  return (size_t)(total / kUpdPerBlock + nseg + 1) * sizeof(float);
+}
+
+extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
+                                              const tn_param_seg *segs, int nseg, int64_t total,
+                                              const int32_t *ctl, float grad_scale,
+                                              const float *nll_sum, float nll_scale,
+                                              float *cost_out, void *workspace, void *stream) {
+  TN_REQUIRE(theta && vel && grad && segs && ctl && workspace, TN_ERR_ARG,
+             "tn_sgd_momentum_maxnorm_update: null argument");
+  TN_REQUIRE(nseg > 0 && nseg <= kMaxSegs, TN_ERR_UNSUPPORTED,
+             "tn_sgd_momentum_maxnorm_update: %d segments (max %d)", nseg, kMaxSegs);
+  SegTable tab;
+  tab.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    tab.seg[s] = segs[s];
+    TN_REQUIRE(segs[s].size > 0 && segs[s].offset >= 0 && segs[s].offset + segs[s].size <= total,
+               TN_ERR_SHAPE, "tn_sgd_momentum_maxnorm_update: segment %d out of range", s);
+    TN_REQUIRE(segs[s].ndim == 1 || (int64_t)segs[s].rows * segs[s].cols == segs[s].size,
+               TN_ERR_SHAPE, "tn_sgd_momentum_maxnorm_update: segment %d rows*cols != size", s);
+  }
+  const int64_t nb = update_blocks(segs, nseg, tab.first_block);
+  cudaStream_t st = (cudaStream_t)stream;
+  float *wt_partial = (float *)workspace;
+  sgd_step_kernel<<<(unsigned)nb, kUpdThreads, 0, st>>>(theta, vel, grad, tab, ctl, grad_scale,
+                                                        wt_partial);
+  TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(step)");
+  for (int s = 0; s < nseg; ++s) {
+    const tn_param_seg &sg = segs[s];
+    if (sg.maxnorm == 0.f || sg.rate == 0.f || sg.ndim == 1) continue;
+    if (sg.ndim == 2) {
+      maxnorm_cols_kernel<<<ceil_div(sg.cols, 32), 256, 0, st>>>(theta + sg.offset, sg.rows,
+                                                                 sg.cols, sg.maxnorm);
+    } else {
+      maxnorm_rows_kernel<<<ceil_div(sg.rows, 8), 256, 0, st>>>(theta + sg.offset, sg.rows,
+                                                                sg.cols, sg.maxnorm);
+    }
+    TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(maxnorm)");
+  }
+  if (cost_out) {
+    finish_cost_kernel<<<1, 256, 0, st>>>(wt_partial, (int)nb, nll_sum, nll_scale, cost_out);
+    TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(cost)");
+  }
+  return TN_OK;
+}

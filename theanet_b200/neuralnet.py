@@ -1,0 +1,661 @@
+"""NeuralNet: theanet's network object (reference: theanet/neuralnet.py:59-333) on hand-written
+sm_100a kernels.
+
+Same constructor (``NeuralNet(layers, training_params, allwts=None)``), same ``get_trin_model`` /
+``get_test_model`` / ``get_data_test_model`` callables, same ``.prms`` vocabulary and ``.pkl``
+schema, so the reference's ``train.py`` loop runs unchanged against it.  What differs is below
+the API: there is no symbolic graph and no autodiff.  The constructor lays all parameters,
+velocities and gradients out in three flat device buffers, allocates one activation tensor per
+layer, and a training step is a fixed sequence of C-ABI kernel launches (forward, softmax-NLL,
+hand-derived backward, one optional NCCL all-reduce of the flat gradient buffer, one fused
+optimiser launch) that is captured once into a CUDA graph and replayed per minibatch.  Per-step
+scalars (step counter, corpus row, learning rate) live in a small device control block that the
+graph refreshes from pinned host memory.
+
+PyTorch is used for device memory, streams, CUDA graphs and torch.distributed only.
+"""
+import ctypes
+from functools import reduce
+from operator import mul
+
+import numpy as np
+import torch
+
+from . import _C
+from . import layer
+from .layer import (InputLayer, ElasticLayer, ConvLayer, PoolLayer, DropOutLayer, HiddenLayer,
+                    SoftmaxLayer)
+
+# ########################### Helper Functions #################################
+
+
+def get_layers_info(layers):
+    lines = []
+    for name, args in layers:
+        lines.append('\n{} : '.format(name))
+        lines.extend('\n\t{} : \t{}'.format(k, args[k]) for k in args)
+    return ''.join(lines)
+
+
+def get_wts_info(wts, detailed=False):
+    out, n_wts = [], 0
+    for l, ww in enumerate(wts):
+        out.append("\nLayer {}:".format(l))
+        for w in ww:
+            n_ww = reduce(mul, w.shape)
+            n_wts += n_ww
+            out.append('\n\t {} {} ❲{}❳'.format(w.shape, w.dtype, n_ww))
+            if detailed:
+                out.append(" ❲{:.2e}, {:.2e}, {:.2e}❳".format(w.min(), w.mean(), w.max()))
+    out.append('\n\nTotal Number of Weights : {:,}'.format(n_wts))
+    return ''.join(out)
+
+
+def get_training_params_info(training_params):
+    return "Training Parameters:" + ''.join(
+        '\n\t{} : \t{}'.format(k, training_params[k]) for k in sorted(training_params.keys()))
+
+
+class _Scalar:
+    """Stand-in for the reference's shared learning-rate scalar (neuralnet.py:110)."""
+
+    def __init__(self, v=0.0):
+        self.v = np.float32(v)
+
+    def set_value(self, v):
+        self.v = np.float32(v)
+
+    def get_value(self):
+        return self.v
+
+
+def _as_numpy(data):
+    if hasattr(data, 'get_value'):
+        data = data.get_value()
+    if isinstance(data, torch.Tensor):
+        return data
+    return np.asarray(data)
+
+
+class DistContext:
+    """Data-parallel context: one process per GPU, torch.distributed for the plumbing."""
+
+    def __init__(self, rank=0, world=1, group=None):
+        self.rank, self.world, self.group = rank, world, group
+
+    def all_reduce_sum(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
+
+
+###############################################################################
+#                           The Neural Network
+###############################################################################
+
+
+class NeuralNet():
+    def __init__(self, layers, training_params, allwts=None, test_x=None, device=None, dist=None,
+                 use_graph=True):
+        if allwts is None:
+            self.rand_gen = np.random.RandomState(training_params['SEED'])
+        else:
+            self.rand_gen = None
+        self.tr_prms = training_params
+        self.layers = layers
+        self.allwts = allwts
+        self.tr_layers = []
+        self.te_layers = []
+        self.dist = dist or DistContext()
+        self.batch_sz = training_params['BATCH_SZ']          # global minibatch
+        assert self.batch_sz % self.dist.world == 0, "BATCH_SZ must divide by the world size"
+        self.local_bsz = self.batch_sz // self.dist.world
+        self.num_layers = 0
+        if device is None:
+            device = 'cuda' if torch.cuda.is_available() else 'cpu'
+        self.device = torch.device(device)
+        self.use_graph = use_graph and self.device.type == 'cuda'
+
+        # Input Layer
+        input_layer_type = getattr(layer, layers[0][0])
+        assert input_layer_type in (InputLayer, ElasticLayer), \
+            "First layer needs to be Input or Elastic Layer"
+        self.tr_layers.append(input_layer_type(None, rand_gen=self.rand_gen, **layers[0][1]))
+        self.te_layers.append(self.tr_layers[0].TestVersion(None))
+        self.num_layers += 1
+        while self.num_layers < len(layers):
+            self.append_next_layer()
+        assert isinstance(self.tr_layers[-1], SoftmaxLayer), "last layer must be a SoftmaxLayer"
+
+        if 'CUR_EPOCH' not in training_params:
+            training_params['CUR_EPOCH'] = 0
+        self.cur_learn_rate = _Scalar(0.0)
+        self.set_rate()
+
+        self.step_count = 0
+        self.inject = {}            # (layer index, 'noise'|'u'|'flip'|'mask') -> device tensor
+        self.debug_elastic = False
+        self._allocate()
+
+    # ------------------------------------------------------------------------------------------
+    def append_next_layer(self):
+        layer_type, layer_args = self.layers[self.num_layers]
+        prev_tr_layer = self.tr_layers[self.num_layers - 1]
+        prev_te_layer = self.te_layers[self.num_layers - 1]
+        wts = self.allwts[self.num_layers] if self.allwts else None
+        tr_inpt, te_inpt = prev_tr_layer.output, prev_te_layer.output
+        curr_layer_type = getattr(layer, layer_type, None)
+
+        if curr_layer_type in (ConvLayer, PoolLayer):
+            # a DropOutLayer carries no map geometry: look through it (neuralnet.py:123-130)
+            use = self.tr_layers[self.num_layers - 2] if type(prev_tr_layer) is DropOutLayer \
+                else prev_tr_layer
+            num_prev_maps, prev_out_sz = use.num_maps, use.out_sz
+
+        if curr_layer_type is ConvLayer:
+            curr_layer = ConvLayer(tr_inpt, wts, self.rand_gen, self.batch_sz, num_prev_maps,
+                                   prev_out_sz, **layer_args)
+        elif curr_layer_type is PoolLayer:
+            curr_layer = PoolLayer(tr_inpt, num_maps=num_prev_maps, in_sz=prev_out_sz,
+                                   **layer_args)
+        elif curr_layer_type is DropOutLayer:
+            curr_layer = DropOutLayer(tr_inpt, self.rand_gen, prev_tr_layer.n_out, **layer_args)
+        elif curr_layer_type in (HiddenLayer, SoftmaxLayer):
+            te_inpt = te_inpt.flatten(2)
+            curr_layer = curr_layer_type(tr_inpt.flatten(2), wts, self.rand_gen,
+                                         prev_tr_layer.n_out, **layer_args)
+        else:
+            raise NotImplementedError("Unknown Layer Type" + layer_type)
+
+        self.tr_layers.append(curr_layer)
+        self.te_layers.append(curr_layer.TestVersion(te_inpt))
+        self.num_layers += 1
+
+    # ------------------------------------------------------------------------------------------
+    # memory layout
+    # ------------------------------------------------------------------------------------------
+    def _allocate(self):
+        dev, B = self.device, self.local_bsz
+        f32 = torch.float32
+        # flat parameter / velocity / gradient buffers; every tensor starts on a 16-byte boundary
+        params = []
+        for lyr in self.tr_layers:
+            for p in lyr.params:
+                if p not in params:
+                    params.append(p)
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.size + 3) // 4 * 4
+        self.n_flat = total
+        self.theta = torch.zeros(total, dtype=f32, device=dev)
+        self.vel = torch.zeros(total, dtype=f32, device=dev)
+        # gradient buffer + 4 trailing floats: [nll partial sum, pad]; one all-reduce covers both
+        self.grad = torch.zeros(total + 4, dtype=f32, device=dev)
+        self.nll_sum = self.grad[total:total + 1]
+        self.params = params
+        self.param_offset = dict()
+        for p, o in zip(params, offs):
+            shp = p.shape
+            p.bind(self.theta[o:o + p.size].view(shp), self.vel[o:o + p.size].view(shp),
+                   self.grad[o:o + p.size].view(shp))
+            self.param_offset[id(p)] = o
+        # optimiser segment table (theanet/layer/layer.py:70-107)
+        segs = []
+        for lyr in self.tr_layers:
+            for p, reg in lyr.update_segments():
+                s = _C.ParamSeg()
+                s.offset, s.size, s.ndim = self.param_offset[id(p)], p.size, p.ndim
+                if p.ndim == 2:
+                    s.rows, s.cols = p.shape
+                elif p.ndim == 4:
+                    s.rows, s.cols = p.shape[0], p.size // p.shape[0]
+                else:
+                    s.rows, s.cols = 1, p.size
+                s.momentum, s.rate = reg['momentum'], reg['rate'] or 0
+                s.maxnorm, s.l1, s.l2 = reg['maxnorm'] or 0, reg['L1'], reg['L2']
+                segs.append(s)
+        self.segs = (_C.ParamSeg * max(1, len(segs)))(*segs)
+        self.n_segs = len(segs)
+        trainable = [bool(getattr(l, 'reg', None) and l.reg['rate'] and l.params)
+                     for l in self.tr_layers]
+        self.trainable = trainable
+        # need_below[li]: some trainable layer sits strictly below li
+        self.need_below = [any(trainable[:li]) for li in range(len(self.tr_layers))]
+
+        # activations (shared by the train and test twins), gradient buffers
+        self.out, self.dbuf = [], []
+        for li, lyr in enumerate(self.tr_layers):
+            shp = (B,) + lyr.output.shape
+            t = torch.empty(shp, dtype=f32, device=dev)
+            self.out.append(t)
+            lyr.output.tensor = t
+            self.te_layers[li].output.tensor = t
+            need = li + 1 < len(self.tr_layers) and self.need_below[li + 1]
+            self.dbuf.append(torch.empty(shp, dtype=f32, device=dev) if need else None)
+        last = self.tr_layers[-1]
+        n_out = last.n_out
+        self.z = self.out[-1]                                   # pre-softmax scores
+        self.logprob = torch.empty((B, n_out), dtype=f32, device=dev)
+        self.gsoft = torch.empty((B, n_out), dtype=f32, device=dev)
+        self.rowloss = torch.empty(B, dtype=f32, device=dev)
+        self.cost = torch.zeros(1, dtype=f32, device=dev)
+        self.stats = torch.zeros(2 + 2 * B, dtype=f32, device=dev)
+        self.preds = torch.zeros(B, dtype=torch.int64, device=dev)
+        for l in (last, self.te_layers[-1]):
+            l.logprob.tensor = self.logprob
+            l.y_preds.tensor = self.preds
+        # control block: pinned host copy -> device, refreshed inside the captured graph
+        pin = self.device.type == 'cuda'
+        self.ctl_host = torch.zeros(_C.CTL_WORDS, dtype=torch.int32, pin_memory=pin)
+        self.ctl = torch.zeros(_C.CTL_WORDS, dtype=torch.int32, device=dev)
+        self.idx_host = torch.zeros(B, dtype=torch.int32, pin_memory=pin)
+        self.idx = torch.zeros(B, dtype=torch.int32, device=dev)
+        # elastic scratch
+        l0 = self.tr_layers[0]
+        if isinstance(l0, ElasticLayer) and not l0.identity:
+            h = l0.img_sz
+            self.el_noise = torch.zeros(2 * h * h, dtype=f32, device=dev)
+            self.el_gidx = torch.zeros(h * h, dtype=torch.int32, device=dev)
+            self.el_gfrac = torch.zeros(2 * h * h, dtype=f32, device=dev)
+            self.el_target = torch.zeros(2 * h * h, dtype=torch.float64, device=dev)
+            self.el_tyx = torch.zeros(2 * h * h, dtype=torch.float64, device=dev)
+            self.el_filt = torch.from_numpy(l0.filt).to(dev) if l0.filt is not None else None
+            prm = _C.ElasticPrm()
+            prm.h, prm.sigma = h, int(l0.sigma)
+            prm.translation, prm.magnitude = float(l0.translation), float(l0.magnitude)
+            prm.zoom_on = int(l0.zoom != 1)
+            prm.log_zoom = float(np.float32(np.log(l0.zoom)))
+            prm.angle_rad = float(np.float32(l0.angle * np.pi / 180))
+            prm.nearest = int(bool(l0.nearest))
+            prm.clip_hi = h - 1 - .001
+            self.el_prm = prm
+        # workspaces
+        self.ws = {}
+        for li, lyr in enumerate(self.tr_layers):
+            if isinstance(lyr, ConvLayer):
+                nb = _C.lib.tn_conv2d_wgrad_workspace_bytes(B, lyr.num_prev_maps, lyr.in_sz,
+                                                            lyr.num_maps, lyr.filter_sz)
+                self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
+        nb = _C.lib.tn_update_workspace_bytes(max(1, self.n_segs), total)
+        self.ws_update = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
+        self._graphs = {}
+        if self.dist.world > 1:     # replicas must start identical (rank 0 wins)
+            torch.distributed.broadcast(self.theta, src=0, group=self.dist.group)
+
+    # ------------------------------------------------------------------------------------------
+    # launch helpers
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        if self.device.type != 'cuda':
+            raise RuntimeError("theanet_b200 has no CPU execution path: a B200 (sm_100a) device "
+                               "is required to run the network")
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _inj(self, li, kind):
+        t = self.inject.get((li, kind))
+        return _C.ptr(t)
+
+    def _forward(self, layers, train, corpus, idx, labels):
+        """Launch the forward pass of ``layers`` (the train or the test twins)."""
+        st = self._stream()
+        B = self.local_bsz
+        ctl = _C.ptr(self.ctl)
+        idxp = _C.ptr(idx)
+        for li, lyr in enumerate(layers):
+            out = self.out[li]
+            x = self.out[li - 1] if li else None
+            if isinstance(lyr, (InputLayer, ElasticLayer)):
+                if li:
+                    raise NotImplementedError("input-type layers past position 0")
+                # geometry from the TRAIN twin: the reference's Elastic test twin does not forward
+                # num_maps (inlayers.py:157-163), harmless there because it is elementwise
+                C_, h = self.tr_layers[0].num_maps, lyr.out_sz
+                invert = int(getattr(lyr, 'invert', False))
+                mode, gidx, gfrac, pflip, seed = 0, None, None, 0.0, 0
+                if train and isinstance(lyr, ElasticLayer) and not lyr.identity:
+                    seed = lyr.seed
+                    if lyr.has_grid:
+                        noise = self._inj(0, 'noise')
+                        if lyr.magnitude and noise is None:
+                            _C.call('tn_elastic_noise', _C.ptr(self.el_noise), h, seed, ctl, st)
+                            noise = _C.ptr(self.el_noise)
+                        dbg = self.debug_elastic
+                        _C.call('tn_elastic_field', ctypes.byref(self.el_prm), noise,
+                                self._inj(0, 'u'), _C.ptr(self.el_filt), seed, ctl,
+                                _C.ptr(self.el_target) if dbg else None,
+                                _C.ptr(self.el_tyx) if dbg else None,
+                                _C.ptr(self.el_gidx), _C.ptr(self.el_gfrac), st)
+                        mode = 1 if lyr.nearest else 2
+                        gidx, gfrac = _C.ptr(self.el_gidx), _C.ptr(self.el_gfrac)
+                    pflip = float(lyr.pflip)
+                _C.call('tn_elastic_warp', _C.ptr(corpus), idxp, ctl, B, C_, h, invert, mode, gidx,
+                        gfrac, pflip, self._inj(0, 'flip') if train else None, seed, _C.ptr(out),
+                        st)
+            elif isinstance(lyr, ConvLayer):
+                _C.call('tn_conv2d_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor), _C.ptr(lyr.b.tensor),
+                        _C.ptr(out), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz,
+                        lyr.pad_lo, lyr.out_sz, lyr.act.code, lyr.act.nn, st)
+            elif isinstance(lyr, PoolLayer):
+                _C.call('tn_maxpool_fwd', _C.ptr(x), _C.ptr(out), B * lyr.num_maps, lyr.in_sz,
+                        lyr.pool_sz, lyr.out_sz, st)
+            elif isinstance(lyr, DropOutLayer):
+                n = x[0].numel()
+                if train and lyr.pdrop:
+                    _C.call('tn_dropout_apply', _C.ptr(x), _C.ptr(out), B, n, 1. - lyr.pdrop,
+                            lyr.seed, ctl, self._inj(li, 'mask'), 1.0, st)
+                else:
+                    _C.call('tn_dropout_apply', _C.ptr(x), _C.ptr(out), B, n, 1.0, 0, ctl, None,
+                            float(lyr.test_scale), st)
+            elif isinstance(lyr, HiddenLayer):        # incl. SoftmaxLayer (scores only)
+                pkeep = 1. - lyr.pdrop if (train and lyr.pdrop) else 1.0
+                _C.call('tn_dense_fwd', _C.ptr(x), _C.ptr(lyr.w.tensor), _C.ptr(lyr.b.tensor),
+                        _C.ptr(out), B, lyr.n_in, lyr.n_out, lyr.act.code, lyr.act.nn, pkeep,
+                        lyr.seed or 0, ctl, self._inj(li, 'mask') if train else None,
+                        float(lyr.test_scale), st)
+            else:
+                raise NotImplementedError(type(lyr).__name__)
+
+    def _fuse_info(self, li):
+        """How a consumer turns dL/d(out[li]) into dL/dz of layer li inside its own epilogue:
+        (prev_out, act code, nn, pkeep, seed, injected mask) or None when layer li has no
+        activation of its own."""
+        lyr = self.tr_layers[li]
+        if isinstance(lyr, SoftmaxLayer):
+            return None
+        if isinstance(lyr, HiddenLayer):
+            pk = 1. - lyr.pdrop if lyr.pdrop else 1.0
+            return (self.out[li], lyr.act.code, lyr.act.nn, pk, lyr.seed or 0, self._inj(li, 'mask'))
+        if isinstance(lyr, ConvLayer):
+            return (self.out[li], lyr.act.code, lyr.act.nn, 1.0, 0, None)
+        return None
+
+    def _backward(self):
+        st = self._stream()
+        B = self.local_bsz
+        ctl = _C.ptr(self.ctl)
+        L = self.tr_layers
+        g = self.gsoft                       # dL/dz of the layer being visited
+        for li in range(len(L) - 1, 0, -1):
+            lyr = L[li]
+            x = self.out[li - 1]
+            below = self.need_below[li]
+            dx = self.dbuf[li - 1]
+            fuse = self._fuse_info(li - 1) if below else None
+            if isinstance(lyr, HiddenLayer):
+                if self.trainable[li]:
+                    _C.call('tn_dense_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
+                            _C.ptr(lyr.b.grad), B, lyr.n_in, lyr.n_out, st)
+                if below:
+                    po, ac, nn, pk, sd, mi = fuse or (None, 0, 0, 1.0, 0, None)
+                    _C.call('tn_dense_bwd_data', _C.ptr(g), _C.ptr(lyr.w.tensor), _C.ptr(dx), B,
+                            lyr.n_in, lyr.n_out, _C.ptr(po), ac, nn, pk, sd, ctl, mi, st)
+            elif isinstance(lyr, ConvLayer):
+                if self.trainable[li]:
+                    _C.call('tn_conv2d_wgrad', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.W.grad),
+                            _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), B, lyr.num_prev_maps,
+                            lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo, lyr.out_sz, st)
+                if below:
+                    po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, 0, 0)
+                    _C.call('tn_conv2d_dgrad', _C.ptr(g), _C.ptr(lyr.W.tensor), _C.ptr(dx),
+                            _C.ptr(po), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps,
+                            lyr.filter_sz, lyr.pad_lo, lyr.out_sz, ac, nn, st)
+                    if fuse and fuse[3] < 1.0:
+                        raise NotImplementedError("dropout-masked dense output feeding a conv")
+            elif isinstance(lyr, PoolLayer):
+                if below:
+                    ac, nn = (fuse[1], fuse[2]) if fuse else (_C.ACT_LINEAR, 0)
+                    _C.call('tn_maxpool_bwd', _C.ptr(g), _C.ptr(x), _C.ptr(self.out[li]),
+                            _C.ptr(dx), B * lyr.num_maps, lyr.in_sz, lyr.pool_sz, lyr.out_sz, ac,
+                            nn, st)
+                    if fuse and fuse[3] < 1.0:
+                        raise NotImplementedError("dropout-masked dense output feeding a pool")
+            elif isinstance(lyr, DropOutLayer):
+                if below:
+                    n = x[0].numel()
+                    pk = 1. - lyr.pdrop if lyr.pdrop else 1.0
+                    _C.call('tn_dropout_apply', _C.ptr(g), _C.ptr(dx), B, n, pk, lyr.seed or 0, ctl,
+                            self._inj(li, 'mask'), 1.0, st)
+                    if fuse:
+                        po, ac, nn, pkp, sd, mi = fuse
+                        if pkp < 1.0 or mi is not None:
+                            _C.call('tn_dropout_apply', _C.ptr(dx), _C.ptr(dx), B, n, pkp, sd, ctl,
+                                    mi, 1.0, st)
+                        _C.call('tn_act_bwd', _C.ptr(dx), _C.ptr(po), _C.ptr(dx), B * n, ac, nn, st)
+            else:
+                raise NotImplementedError(type(lyr).__name__)
+            if not below:
+                break
+            g = dx
+
+    def _set_ctl(self, row0):
+        c = self.ctl_host
+        c[_C.CTL_STEP] = self.step_count & 0x7fffffff
+        c[_C.CTL_SAMPLE0] = self.dist.rank * self.local_bsz
+        c[_C.CTL_ROW0] = int(row0)
+        c[_C.CTL_LR_BITS] = int(np.float32(self.cur_learn_rate.get_value()).view(np.int32))
+
+    def _train_launches(self, corpus, idx, labels):
+        """Everything one training step enqueues (this is what the CUDA graph captures)."""
+        st = self._stream()
+        B = self.local_bsz
+        self.ctl.copy_(self.ctl_host, non_blocking=True)
+        if idx is not None:
+            self.idx.copy_(self.idx_host, non_blocking=True)
+        self._forward(self.tr_layers, True, corpus, idx, labels)
+        n_out = self.tr_layers[-1].n_out
+        _C.call('tn_softmax_nll_fwd_bwd', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
+                _C.ptr(self.ctl), B, n_out, 1.0 / self.batch_sz, _C.ptr(self.logprob),
+                _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
+        self._backward()
+        _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
+        self.dist.all_reduce_sum(self.grad)          # the one collective of the step
+        _C.call('tn_sgd_momentum_maxnorm_update', _C.ptr(self.theta), _C.ptr(self.vel),
+                _C.ptr(self.grad), self.segs, self.n_segs, self.n_flat, _C.ptr(self.ctl), 1.0,
+                _C.ptr(self.nll_sum), 1.0 / self.batch_sz, _C.ptr(self.cost),
+                _C.ptr(self.ws_update), st)
+
+    def _test_launches(self, corpus, idx, labels):
+        st = self._stream()
+        B = self.local_bsz
+        self.ctl.copy_(self.ctl_host, non_blocking=True)
+        self._forward(self.te_layers, False, corpus, idx, labels)
+        _C.call('tn_softmax_test_stats', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
+                _C.ptr(self.ctl), B, self.tr_layers[-1].n_out, _C.ptr(self.logprob),
+                _C.ptr(self.preds), _C.ptr(self.stats), st)
+        if self.dist.world > 1:
+            self.dist.all_reduce_sum(self.stats[:2])
+
+    def _run(self, key, fn, args, restore=()):
+        """Run ``fn(*args)`` eagerly, or capture it once into a CUDA graph and replay it.
+        ``restore`` lists the tensors whose contents the warm-up execution must not change."""
+        if not self.use_graph or self.inject:
+            fn(*args)
+            return
+        g = self._graphs.get(key)
+        if g is None:
+            snap = [t.clone() for t in restore]
+            fn(*args)                                # warm-up (module loading, NCCL setup)
+            torch.cuda.synchronize(self.device)
+            for t, s in zip(restore, snap):
+                t.copy_(s)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn(*args)
+            self._graphs[key] = g
+        g.replay()
+
+    # ------------------------------------------------------------------------------------------
+    # data staging
+    # ------------------------------------------------------------------------------------------
+    def _stage(self, x_data, y_data, resident):
+        x = _as_numpy(x_data)
+        y = _as_numpy(y_data)
+        l0 = self.tr_layers[0]
+        shp = (-1, l0.num_maps, l0.out_sz, l0.out_sz)
+        if isinstance(x, torch.Tensor):
+            x = x.to(torch.float32).reshape(shp).contiguous()
+        else:
+            x = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32).reshape(shp))
+        if isinstance(y, torch.Tensor):
+            y = y.to(torch.int32).contiguous()
+        else:
+            y = torch.from_numpy(np.ascontiguousarray(y, dtype=np.int32))
+        if resident:
+            return x.to(self.device), y.to(self.device), None
+        if self.device.type == 'cuda':
+            if not x.is_cuda and not x.is_pinned():
+                x = x.pin_memory()
+            if not y.is_cuda and not y.is_pinned():
+                y = y.pin_memory()
+        B = self.local_bsz
+        xb = torch.empty((B,) + tuple(x.shape[1:]), dtype=torch.float32, device=self.device)
+        yb = torch.empty(B, dtype=torch.int32, device=self.device)
+        return xb, yb, (x, y)
+
+    # ------------------------------------------------------------------------------------------
+    # public API (theanet/neuralnet.py:203-296)
+    # ------------------------------------------------------------------------------------------
+    def get_trin_model(self, x_data, y_data, aux_data=None, take_index_list=False, resident=True,
+                       lazy=False):
+        """Returns ``f(batch_index) -> [cost, features, logprob]`` (or ``f(index_vector)`` with
+        take_index_list), the analogue of the reference's compiled training function.
+
+        resident=True keeps the corpus in HBM (the reference keeps it in a Theano shared
+        variable); resident=False leaves it in pinned host memory and copies each minibatch
+        host->device inside the call.  lazy=True returns device tensors without synchronising.
+        """
+        assert aux_data is None, "auxiliary inputs are out of scope"
+        xd, yd, host = self._stage(x_data, y_data, resident)
+        B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
+        key = ('train', id(xd), take_index_list)
+        h_cost = torch.zeros(1, dtype=torch.float32, pin_memory=self.device.type == 'cuda')
+        h_lp = torch.zeros(self.logprob.shape, dtype=torch.float32,
+                           pin_memory=self.device.type == 'cuda')
+
+        def training_fn(indx):
+            if take_index_list:
+                ids = np.asarray(indx, dtype=np.int32)[rank * Bl:(rank + 1) * Bl]
+                if host is None:
+                    self.idx_host.copy_(torch.from_numpy(ids))
+                    idx, row0 = self.idx, 0
+                else:
+                    sel = torch.from_numpy(ids.astype(np.int64))
+                    xd.copy_(host[0][sel], non_blocking=True)
+                    yd.copy_(host[1][sel], non_blocking=True)
+                    idx, row0 = None, 0
+            else:
+                lo = int(indx) * B + rank * Bl
+                if host is None:
+                    idx, row0 = None, lo
+                else:
+                    xd.copy_(host[0][lo:lo + Bl], non_blocking=True)
+                    yd.copy_(host[1][lo:lo + Bl], non_blocking=True)
+                    idx, row0 = None, 0
+            self._set_ctl(row0)
+            self._run(key, self._train_launches, (xd, idx, yd), restore=(self.theta, self.vel))
+            self.step_count += 1
+            if lazy:
+                return self.cost, self.logprob, self.logprob
+            h_cost.copy_(self.cost, non_blocking=True)
+            h_lp.copy_(self.logprob, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            lp = h_lp.numpy().copy()
+            return [h_cost.numpy()[0].copy(), lp, lp]
+
+        return training_fn
+
+    def reset_accumulated_gradients(self):
+        self.vel.zero_()
+
+    def get_test_model(self, x_data, y_data, aux_data=None, preds_feats=False, resident=True):
+        """``f(batch_index) -> (sym_err_rate, mean p[y]) [+ (features, y_preds)]``."""
+        assert aux_data is None, "auxiliary inputs are out of scope"
+        xd, yd, host = self._stage(x_data, y_data, resident)
+        B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
+        key = ('test', id(xd))
+
+        def test_fn(indx):
+            lo = int(indx) * B + rank * Bl
+            if host is None:
+                row0 = lo
+            else:
+                xd.copy_(host[0][lo:lo + Bl], non_blocking=True)
+                yd.copy_(host[1][lo:lo + Bl], non_blocking=True)
+                row0 = 0
+            self._set_ctl(row0)
+            self._run(key, self._test_launches, (xd, None, yd))
+            st = self.stats[:2].cpu().numpy() / self.dist.world
+            outs = [np.float32(st[0]), np.float32(st[1])]
+            if preds_feats:
+                outs += [self.logprob.cpu().numpy(), self.preds.cpu().numpy()]
+            return outs
+
+        return test_fn
+
+    def takes_aux(self):
+        return False
+
+    def get_data_test_model(self, get_output_of_layers=()):
+        """``f(x_batch) -> [features, y_preds, *layer outputs]`` on raw input batches of exactly
+        the (local) batch size (neuralnet.py:282-296)."""
+        Bl = self.local_bsz
+        yd = torch.zeros(Bl, dtype=torch.int32, device=self.device)
+
+        def data_test_fn(x):
+            xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+            assert xd.shape[0] == Bl, "expected a batch of {} images".format(Bl)
+            self._set_ctl(0)
+            self._test_launches(xd.reshape((Bl,) + self.tr_layers[0].output.shape), None, yd)
+            outs = [self.logprob.cpu().numpy(), self.preds.cpu().numpy()]
+            outs += [self.out[i].cpu().numpy() for i in get_output_of_layers]
+            return outs
+
+        return data_test_fn
+
+    def get_init_params(self):
+        return {"layers": self.layers,
+                "training_params": self.tr_prms,
+                "allwts": [l.get_wts() for l in self.tr_layers]}
+
+    def set_rate(self):
+        self.cur_learn_rate.set_value(
+            self.tr_prms['INIT_LEARNING_RATE'] /
+            (1 + self.tr_prms['CUR_EPOCH'] / self.tr_prms['EPOCHS_TO_HALF_RATE']))
+
+    def inc_epoch_set_rate(self):
+        self.tr_prms['CUR_EPOCH'] += 1
+        self.set_rate()
+
+    def get_epoch(self):
+        return self.tr_prms['CUR_EPOCH']
+
+    def __str__(self):
+        prmstr = '; '.join(', '.join(str(p) for p in lyr.params) for lyr in self.tr_layers)
+        return ('\nTrain Layers\n\t' + '\n\t'.join(str(l) for l in self.tr_layers) +
+                '\nTest Layers\n\t' + '\n\t'.join(str(l) for l in self.te_layers) +
+                '\nParams ' + prmstr)
+
+    def get_layers_info(self):
+        return get_layers_info(self.layers)
+
+    def get_wts_info(self, detailed=False):
+        return get_wts_info((l.get_wts() for l in self.tr_layers), detailed)
+
+    def get_training_params_info(self):
+        return get_training_params_info(self.tr_prms)
+
+    # ------------------------------------------------------------------------------------------
+    # extras used by tests / debugging
+    # ------------------------------------------------------------------------------------------
+    def elastic_debugout(self):
+        """[displacement (2,h,h) float64, clipped coordinates (2,h,h)] of the last training step
+        (needs ``debug_elastic = True``), cf. ElasticLayer.debugout (inlayers.py:145-155)."""
+        h = self.tr_layers[0].img_sz
+        tgt = self.el_target.cpu().numpy().reshape(2, h, h)
+        return [tgt - np.indices((h, h)), self.el_tyx.cpu().numpy().reshape(2, h, h)]
+
+    def get_velocities(self):
+        return [[p.vel.detach().cpu().numpy().copy() for p in l.params] for l in self.tr_layers]
+
+    def get_gradients(self):
+        return [[p.grad.detach().cpu().numpy().copy() for p in l.params] for l in self.tr_layers]
