@@ -31,11 +31,23 @@ def C():
     return _C
 
 
+_KEEP = []      # device tensors whose raw pointers were handed to the C ABI stay alive per test
+
+
+@pytest.fixture(autouse=True)
+def _release_device_tensors():
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
 def dev(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
     if dtype is not None:
         t = t.to(dtype)
-    return t.cuda()
+    t = t.cuda()
+    _KEEP.append(t)
+    return t
 
 
 def make_ctl(C, step=0, sample0=0, row0=0, lr=0.1):

@@ -81,7 +81,7 @@ def compare_nets(net, on, tag):
                 '{} velocity layer {} tensor {}: {}'.format(tag, li, k, r)
 
 
-def run_pair(prms, x, y, steps, use_graph, check_at=(1, 2, 5), **trin_kw):
+def run_pair(prms, x, y, steps, use_graph, check_at=(1, 2, 5), frozen_first=True, **trin_kw):
     from theanet_b200.neuralnet import NeuralNet
     p_dev, p_cpu = copy.deepcopy(prms), copy.deepcopy(prms)
     net = NeuralNet(p_dev['layers'], p_dev['training_params'], use_graph=use_graph)
@@ -99,7 +99,7 @@ def run_pair(prms, x, y, steps, use_graph, check_at=(1, 2, 5), **trin_kw):
         assert rel(lp, olp) < TOL, 'step {} logprob {}'.format(s, rel(lp, olp))
         assert feats is lp or np.array_equal(feats, lp)
         costs.append((float(cost), float(ocost)))
-        if s == 0:      # lagged momentum: nothing moves on the first step
+        if s == 0 and frozen_first:      # lagged momentum: nothing moves on the first step
             for a, b in zip(init, net.get_init_params()['allwts']):
                 for u, v in zip(a, b):
                     assert np.array_equal(u, v)
@@ -136,8 +136,9 @@ def test_small_net_all_layer_kinds_bilinear_maxnorm_l1():
     prms = copy.deepcopy(SMALL_NET)
     prms['layers'][0][1]['img_sz'] = 17
     x, y = synth(16 * 3, 3, 17, 11)
-    run_pair(prms, x, y, 12, False)
-    run_pair(prms, x, y, 12, True)
+    # maxnorm rescales the initial filters on step 1, so the 'nothing moves' check is off here
+    run_pair(prms, x, y, 12, False, frozen_first=False)
+    run_pair(prms, x, y, 12, True, frozen_first=False)
 
 
 def test_graph_and_eager_are_bit_identical_and_host_streaming_matches():
