@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the theanet CNN-training hot path on B200 (BASELINE.json metric: images/sec of the
+full training step on mnist.prms-shaped synthetic 28x28x1 batches, 1024 images per GPU, fp32).
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun)
+    python bench.py --impl reference ...                      CPU reference arm (oracle port)
+
+One step = elastic distortion + forward + softmax-NLL + backward + (N>1: one NCCL all-reduce of
+the flat gradient buffer) + fused momentum/maxnorm update over one minibatch.  Prints ONE JSON
+line (rank 0).  `value` is timed with the corpus resident in HBM; `e2e` goes through the public
+get_trin_model() callable with HOST (pinned) buffers: per step one host->device copy of the
+minibatch and a device->host read of cost + log-probabilities.
+"""
+import argparse
+import ast
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PER_GPU_BATCH = 1024
+IMG, NCLS = 28, 10
+CORPUS_BATCHES = 64                # 64 x 1024 x 3136 B = 205 MB per GPU-share: larger than L2
+WORKLOAD = "params/mnist.prms synthetic 28x28x1, batch 1024 per GPU, fp32 (BASELINE configs[1])"
+# algorithmic work of one training step, per image (layer-boundary convention)
+FLOP_PER_IMG = 2810064
+BYTES_PER_IMG = 181144
+PARAM_BYTES_PER_STEP = 8 * 4 * 366290
+
+
+def load_prms(global_batch):
+    with open(os.path.join(ROOT, 'params', 'mnist.prms')) as f:
+        p = ast.literal_eval(f.read())
+    p['training_params'].update(SEED=555555, BATCH_SZ=global_batch)
+    p['layers'][0][1]['img_sz'] = IMG
+    return p
+
+
+def synth_corpus(n):
+    """uniform pixels thresholded so ~80% are exactly 0, uniform labels."""
+    rng = np.random.default_rng(1234)
+    x = rng.random((n, 1, IMG, IMG), dtype=np.float32)
+    x *= (x > .8)
+    y = rng.integers(0, NCLS, n).astype(np.int32)
+    return x, y
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            m = json.load(f)
+        return float(m['hbm_gbs']), float(m['bf16_tflops']), 'measured (MEASURED_PEAKS.json)'
+    except Exception:
+        return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                    '--format=csv,noheader,nounits'], capture_output=True,
+                                   text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        self.stop_flag = True
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k] == 'Active' for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_time(budget_s, batch, steps=None, warmup=1):
+    """images/s of oracle.OracleNet.train_step (numpy + BLAS, all host threads) on `batch`-image
+    minibatches of the same workload."""
+    from oracle import theanet_oracle as O          # checker / baseline only
+    p = load_prms(batch)
+    on = O.OracleNet(p['layers'], p['training_params'])
+    x, y = synth_corpus(batch * 2)
+    for s in range(warmup):
+        on.train_step(x[:batch], y[:batch], step=s)
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        i = n % 2
+        on.train_step(x[i * batch:(i + 1) * batch], y[i * batch:(i + 1) * batch], step=warmup + n)
+        n += 1
+        if steps is not None:
+            if n >= steps:
+                break
+        elif time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n * batch / dt, n, dt
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    batch = 256                                   # bounded sample: 256-image minibatches
+    steps = max(1, args.steps)
+    v, n, dt = cpu_step_time(None, batch, steps=steps, warmup=max(1, min(args.warmup, 3)))
+    cores = host_threads()
+    sample = "{} oracle train steps of {} images (numpy/BLAS im2col+SGEMM restatement)".format(n, batch)
+    line = {
+        "impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cpu_sample_batch": batch},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# per-entry-point algorithmic work (for the dominant-kernel roofline)
+# ------------------------------------------------------------------------------------------------
+def stage_work(net):
+    """name -> (algorithmic bytes, flops) per launch group for the layers of `net`."""
+    from theanet_b200.layer import ConvLayer, HiddenLayer, PoolLayer
+    B = net.local_bsz
+    w = {}
+    for li, l in enumerate(net.tr_layers):
+        if isinstance(l, ConvLayer):
+            xin = B * l.num_prev_maps * l.in_sz ** 2 * 4
+            yout = B * l.num_maps * l.out_sz ** 2 * 4
+            wt = l.W.size * 4
+            fl = 2 * B * l.num_maps * l.out_sz ** 2 * l.num_prev_maps * l.filter_sz ** 2
+            w[('tn_conv2d_fprop', li)] = (xin + yout + wt, fl)
+            w[('tn_conv2d_dgrad', li)] = (xin + yout + wt, fl)
+            w[('tn_conv2d_wgrad', li)] = (xin + yout + wt, fl)
+        elif isinstance(l, PoolLayer):
+            xin = B * l.num_maps * l.in_sz ** 2 * 4
+            yout = B * l.num_maps * l.out_sz ** 2 * 4
+            w[('tn_maxpool_fwd', li)] = (xin + yout, 0)
+            w[('tn_maxpool_bwd', li)] = (2 * xin + 2 * yout, 0)
+        elif isinstance(l, HiddenLayer):
+            a, b_, c = B * l.n_in * 4, l.n_in * l.n_out * 4, B * l.n_out * 4
+            fl = 2 * B * l.n_in * l.n_out
+            w[('tn_dense_fwd', li)] = (a + b_ + c, fl)
+            w[('tn_dense_bwd_data', li)] = (2 * a + b_ + c, fl)
+            w[('tn_dense_bwd_weights', li)] = (a + b_ + c, fl)
+    return w
+
+
+def profile_stages(net, fn, nb, reps):
+    """Time every C-ABI call of the training step with CUDA events on the launching stream
+    (eager execution, graphs off), `reps` steps.  Returns {(entry point, ordinal): mean ms}."""
+    import torch
+    from theanet_b200 import _C
+    records = {}
+    orig = _C.call
+    counter = {}
+
+    def timed_call(name, *a):
+        k = counter.get(name, 0)
+        counter[name] = k + 1
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(name, *a)
+        e.record()
+        records.setdefault((name, k), []).append((s, e))
+
+    import theanet_b200.neuralnet as nnmod
+    saved = net.use_graph
+    net.use_graph = False
+    _C.call = timed_call
+    nnmod._C.call = timed_call
+    try:
+        for r in range(reps + 1):
+            counter.clear()
+            if r == 0:
+                records.clear()
+            fn(r % nb)
+        torch.cuda.synchronize()
+    finally:
+        _C.call = orig
+        nnmod._C.call = orig
+        net.use_graph = saved
+    out = {}
+    for k, evs in records.items():
+        ts = [s.elapsed_time(e) for s, e in evs[1:]] or [evs[0][0].elapsed_time(evs[0][1])]
+        out[k] = float(np.mean(ts))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from theanet_b200.neuralnet import NeuralNet, DistContext
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    assert world == args.gpus or world == 1, "--gpus must match the torchrun world size"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    ctx = DistContext()
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        ctx = DistContext(rank, world, None)
+
+    gb = PER_GPU_BATCH * world
+    prms = load_prms(gb)
+    x, y = synth_corpus(CORPUS_BATCHES * gb)
+    net = NeuralNet(prms['layers'], prms['training_params'], device=dev, dist=ctx)
+    fn = net.get_trin_model(x, y, lazy=True)
+    nb = CORPUS_BATCHES
+    warm = max(3, args.warmup)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for s in range(warm):
+        fn(s % nb)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0 = net.step_count
+    e0.record()
+    for s in range(args.steps):
+        fn((warm + s) % nb)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.summary() if rank == 0 else None
+    launches = int(net.launches.get('train', 0)) * (net.step_count - n0)
+    value = args.steps * gb / (ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers --------------------------------
+    xh = torch.from_numpy(x).pin_memory()
+    yh = torch.from_numpy(y).pin_memory()
+    fn_e2e = net.get_trin_model(xh, yh, resident=False, lazy=False)
+    for s in range(warm):
+        fn_e2e(s % nb)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        cost, feats, _ = fn_e2e((warm + s) % nb)
+    torch.cuda.synchronize(dev)
+    dt = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    Bl = net.local_bsz
+    e2e = {"value": args.steps * gb / dt, "unit": "images/s",
+           "h2d_bytes_per_step": world * (Bl * IMG * IMG * 4 + Bl * 4 + 32),
+           "d2h_bytes_per_step": world * (4 + Bl * NCLS * 4),
+           "ms_per_step": 1e3 * dt / args.steps,
+           "api": "NeuralNet.get_trin_model(x_host, y_host, resident=False)(batch_index)"}
+    assert np.isfinite(float(cost))
+
+    # ---- dominant kernel, timed live with CUDA events ------------------------------------------
+    roof = None
+    hbm, tfl, which = peaks()
+    if rank == 0 or world > 1:
+        fn_prof = net.get_trin_model(x, y, lazy=True)
+        stages = profile_stages(net, fn_prof, nb, reps=10)
+        if rank == 0:
+            work = stage_work(net)
+            # ordinal -> layer index per entry point, in call order
+            order = {}
+            from theanet_b200.layer import ConvLayer, HiddenLayer, PoolLayer
+            L = net.tr_layers
+            order['tn_conv2d_fprop'] = [i for i, l in enumerate(L) if isinstance(l, ConvLayer)]
+            order['tn_maxpool_fwd'] = [i for i, l in enumerate(L) if isinstance(l, PoolLayer)]
+            order['tn_dense_fwd'] = [i for i, l in enumerate(L) if isinstance(l, HiddenLayer)]
+            order['tn_dense_bwd_weights'] = order['tn_dense_fwd'][::-1]
+            order['tn_dense_bwd_data'] = order['tn_dense_fwd'][::-1]
+            order['tn_conv2d_wgrad'] = order['tn_conv2d_fprop'][::-1]
+            order['tn_conv2d_dgrad'] = order['tn_conv2d_fprop'][::-1][:-1]
+            order['tn_maxpool_bwd'] = order['tn_maxpool_fwd'][::-1]
+            total_ms = sum(stages.values())
+            (name, k), t_ms = max(stages.items(), key=lambda kv: kv[1])
+            li = order.get(name, [None] * (k + 1))[k] if name in order else None
+            byts, fl = work.get((name, li), (None, None))
+            share = {"{}#{}".format(n_, k_): round(v / total_ms, 4)
+                     for (n_, k_), v in sorted(stages.items(), key=lambda kv: -kv[1])[:8]}
+            if byts is not None:
+                ach = byts / (t_ms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "kernel": "{} (layer {})".format(name, li),
+                        "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                        "traffic": None, "launch_ms": t_ms, "algorithmic_bytes": byts,
+                        "algorithmic_flops": fl,
+                        "achieved_tflops": (fl / (t_ms * 1e-3) / 1e12) if fl else None,
+                        "peak_source": which, "step_share": share,
+                        "eager_step_ms_sum": total_ms}
+            else:
+                roof = {"bound": "hbm", "kernel": name, "achieved": None, "peak": hbm,
+                        "unit": "GB/s", "frac": None, "traffic": None, "launch_ms": t_ms,
+                        "peak_source": which, "step_share": share}
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # whole-step view against the HBM roofline (SURVEY.md 8d figures)
+    step_bytes = BYTES_PER_IMG * PER_GPU_BATCH + PARAM_BYTES_PER_STEP
+    step_gbs = step_bytes / (ms / args.steps * 1e-3) / 1e9
+
+    cpu_v, cpu_n, cpu_dt = (None, 0, 0.0)
+    cpu = None
+    if world == 1:
+        cpu_v, cpu_n, cpu_dt = cpu_step_time(12.0, 256)
+        cpu = {"value": cpu_v, "unit": "images/s", "cores": host_threads(), "kind": "port",
+               "sample": "{} oracle train steps of 256 images in {:.1f} s (numpy/BLAS "
+                         "restatement of the Theano CPU path)".format(cpu_n, cpu_dt)}
+
+    line = {
+        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": PER_GPU_BATCH,
+                   "parallelism": "dp{}".format(world),
+                   "l2": "corpus of {} minibatches ({} MB per GPU) cycled, larger than the 126 MB "
+                         "L2; no explicit flush".format(nb, nb * PER_GPU_BATCH * IMG * IMG * 4 // 10 ** 6),
+                   "cuda_graph": bool(net.use_graph)},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+        "roofline": roof, "cpu_baseline": cpu,
+        "step_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes,
+                          "achieved": step_gbs, "peak": hbm, "unit": "GB/s",
+                          "frac": step_gbs / hbm, "flop_per_img": FLOP_PER_IMG},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -61,6 +61,8 @@ enum { TN_RNG_DROPOUT = 0, TN_RNG_FLIP = 1, TN_RNG_NOISE = 2, TN_RNG_SCALARS = 3
 
 int tn_version(void);
 const char *tn_last_error(void);
+/* number of kernels this library has launched (or recorded into a graph capture) so far */
+uint64_t tn_launch_count(void);
 /* refuses anything that is not compute capability 10.x */
 int tn_device_check(int device);
 
@@ -157,7 +159,7 @@ int tn_softmax_nll_fwd_bwd(const float *z, const int32_t *y, const int32_t *idx,
                            const int32_t *ctl, int B, int n, float inv_global_batch,
                            float *logprob, float *g, float *rowloss, void *stream);
 /* test twin: logprob, preds = argmax (first maximum, int64), stats[0] = mean(pred != y),
- * stats[1] = mean(p[y])  (outlayers.py:69-80) */
+ * stats[1] = mean(p[y])  (outlayers.py:69-80).  stats is float[2 + 2*B]; the tail is scratch. */
 int tn_softmax_test_stats(const float *z, const int32_t *y, const int32_t *idx,
                           const int32_t *ctl, int B, int n, float *logprob, int64_t *preds,
                           float *stats, void *stream);

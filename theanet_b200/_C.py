@@ -41,6 +41,7 @@ _I64 = C.c_int64
 SIGNATURES = {
     'tn_version': (_I, []),
     'tn_last_error': (C.c_char_p, []),
+    'tn_launch_count': (C.c_uint64, []),
     'tn_device_check': (_I, [_I]),
     'tn_philox_words': (_I, [_P, _I, _I, _U64, _I, _I, _I, _P]),
     'tn_elastic_noise': (_I, [_P, _I, _U64, _P, _P]),

@@ -8,6 +8,9 @@
 namespace tn {
 
 static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -78,6 +81,8 @@ using namespace tn;
 extern "C" int tn_version(void) { return TN_VERSION; }
 
 extern "C" const char *tn_last_error(void) { return g_err; }
+
+extern "C" uint64_t tn_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
 extern "C" int tn_device_check(int device) {
   cudaDeviceProp p;

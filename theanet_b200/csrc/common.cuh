@@ -10,6 +10,7 @@
 namespace tn {
 
 void set_error(const char *fmt, ...);
+void count_launch();   // bumps the counter behind tn_launch_count()
 
 #define TN_REQUIRE(cond, code, ...)      \
   do {                                   \
@@ -26,6 +27,7 @@ void set_error(const char *fmt, ...);
       tn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));      \
       return TN_ERR_CUDA;                                                         \
     }                                                                             \
+    tn::count_launch();                                                           \
   } while (0)
 
 constexpr int kNumSM = 148;

@@ -279,6 +279,7 @@ class NeuralNet():
         nb = _C.lib.tn_update_workspace_bytes(max(1, self.n_segs), total)
         self.ws_update = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
         self._graphs = {}
+        self.launches = {}          # 'train' / 'test' -> kernels of this library per step
         if self.dist.world > 1:     # replicas must start identical (rank 0 wins)
             torch.distributed.broadcast(self.theta, src=0, group=self.dist.group)
 
@@ -469,12 +470,16 @@ class NeuralNet():
         """Run ``fn(*args)`` eagerly, or capture it once into a CUDA graph and replay it.
         ``restore`` lists the tensors whose contents the warm-up execution must not change."""
         if not self.use_graph or self.inject:
+            n0 = _C.lib.tn_launch_count()
             fn(*args)
+            self.launches[key[0]] = _C.lib.tn_launch_count() - n0
             return
         g = self._graphs.get(key)
         if g is None:
             snap = [t.clone() for t in restore]
+            n0 = _C.lib.tn_launch_count()
             fn(*args)                                # warm-up (module loading, NCCL setup)
+            self.launches[key[0]] = _C.lib.tn_launch_count() - n0   # kernels per replay
             torch.cuda.synchronize(self.device)
             for t, s in zip(restore, snap):
                 t.copy_(s)
