@@ -220,16 +220,26 @@ __global__ void __launch_bounds__(1024) conv_wgrad_kernel(WgradArgs a) {
   }
 }
 
-// final[o] = sum over CTAs (fixed order); scatter into dW (OIHW, flipped back) and db
-__global__ void conv_wgrad_finish_kernel(const float *__restrict__ partial, int nblk, int C, int M,
-                                         int f, float *__restrict__ dW, float *__restrict__ db) {
+// final[o] = sum over CTAs (fixed order); scatter into dW (OIHW, flipped back) and db.
+// 32 outputs x 32 slices of the CTA partials per block, slices combined in a fixed order.
+__global__ void __launch_bounds__(1024)
+conv_wgrad_finish_kernel(const float *__restrict__ partial, int nblk, int C, int M, int f,
+                         float *__restrict__ dW, float *__restrict__ db) {
+  __shared__ float red[32][33];
   const int G = (M + 3) >> 2, mP = 4 * G;
   const int OG = G * C * f * f;
   const int stride = OG * 4 + mP;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= stride) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + tx;
   float s = 0.f;
-  for (int k = 0; k < nblk; ++k) s += partial[(size_t)k * stride + o];
+  if (o < stride)
+    for (int k = ty; k < nblk; k += 32) s += partial[(size_t)k * stride + o];
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || o >= stride) return;
+  s = red[0][tx];
+#pragma unroll
+  for (int q = 1; q < 32; ++q) s += red[q][tx];
   if (o < OG * 4) {
     const int q = o & 3, og = o >> 2;
     const int v = og % f;
@@ -311,7 +321,7 @@ extern "C" int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float
   k<<<grid, threads, smem, st>>>(a);
   TN_LAUNCH_CHECK("tn_conv2d_wgrad");
   const int n = OG * 4 + mP;
-  conv_wgrad_finish_kernel<<<ceil_div(n, 128), 128, 0, st>>>((const float *)workspace, grid, C, M,
+  conv_wgrad_finish_kernel<<<ceil_div(n, 32), 1024, 0, st>>>((const float *)workspace, grid, C, M,
                                                               f, dW, db);
   TN_LAUNCH_CHECK("tn_conv2d_wgrad(finish)");
   return TN_OK;

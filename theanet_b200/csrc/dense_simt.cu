@@ -9,6 +9,7 @@
 // float32 FFMA keeps the fp32 configs (C1-C3, C5) inside the 1e-3 parity budget without any
 // tensor-core input rounding; the bf16 config uses the tcgen05 path (gemm_tc.cu).
 #include "common.cuh"
+#include "dense_small.cuh"
 
 namespace tn {
 
@@ -220,20 +221,21 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(GemmArgs g) {
   }
 }
 
-// db[n] = sum_b g[b,n]; 32 columns x 8 row-slices per CTA, slices combined in a fixed order
-__global__ void colsum_kernel(const float *__restrict__ g, float *__restrict__ db, int B, int N) {
-  __shared__ float red[8][33];
+// db[n] = sum_b g[b,n]; 32 columns x 32 row-slices per CTA, slices combined in a fixed order
+__global__ void __launch_bounds__(1024) colsum_kernel(const float *__restrict__ g,
+                                                      float *__restrict__ db, int B, int N) {
+  __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
   float s = 0.f;
   if (n < N)
-    for (int b = ty; b < B; b += 8) s += g[(size_t)b * N + n];
+    for (int b = ty; b < B; b += 32) s += g[(size_t)b * N + n];
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && n < N) {
     float r = red[0][tx];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) r += red[q][tx];
+    for (int q = 1; q < 32; ++q) r += red[q][tx];
     db[n] = r;
   }
 }
@@ -264,12 +266,17 @@ extern "C" int tn_dense_fwd(const float *x, const float *W, const float *bias, f
                             void *stream) {
   TN_REQUIRE(x && W && bias && out, TN_ERR_ARG, "tn_dense_fwd: null argument");
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0, TN_ERR_SHAPE, "tn_dense_fwd: bad shape");
+  TN_REQUIRE(mask_mode(pkeep, mask_inj) != 1 || ctl, TN_ERR_ARG, "tn_dense_fwd: dropout needs ctl");
+  if (dense_small_ok(n_in, n_out)) {
+    SmallArgs a{x, W, bias, nullptr, mask_inj, out, ctl, seed, bernoulli_threshold(pkeep),
+                mask_mode(pkeep, mask_inj), act, (float)act_nn, out_scale, B, n_in, n_out};
+    return dense_fwd_small(a, (cudaStream_t)stream);
+  }
   GemmArgs g{};
   g.A = x; g.B = W; g.C = out;
   g.M = B; g.N = n_out; g.K = n_in; g.lda = n_in; g.ldb = n_out; g.ldc = n_out;
   g.bias = bias; g.mask_inj = mask_inj; g.ctl = ctl; g.seed = seed;
   g.mask_on = mask_mode(pkeep, mask_inj);
-  TN_REQUIRE(g.mask_on != 1 || ctl, TN_ERR_ARG, "tn_dense_fwd: dropout needs ctl");
   g.thr = bernoulli_threshold(pkeep);
   g.act = act; g.act_nn = (float)act_nn; g.scale = out_scale;
   const bool vec = n_in % 4 == 0 && n_out % 4 == 0 && aligned16(x) && aligned16(W) && aligned16(out);
@@ -282,6 +289,13 @@ extern "C" int tn_dense_bwd_data(const float *gr, const float *W, float *dx, int
                                  const float *mask_inj_prev, void *stream) {
   TN_REQUIRE(gr && W && dx, TN_ERR_ARG, "tn_dense_bwd_data: null argument");
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0, TN_ERR_SHAPE, "tn_dense_bwd_data: bad shape");
+  if (dense_small_ok(n_in, n_out)) {
+    const int mo = prev_out ? mask_mode(pkeep_prev, mask_inj_prev) : 0;
+    TN_REQUIRE(mo != 1 || ctl, TN_ERR_ARG, "tn_dense_bwd_data: dropout needs ctl");
+    SmallArgs a{gr, W, nullptr, prev_out, mask_inj_prev, dx, ctl, seed_prev,
+                bernoulli_threshold(pkeep_prev), mo, act_prev, (float)nn_prev, 1.f, B, n_in, n_out};
+    return dense_bwd_data_small(a, (cudaStream_t)stream);
+  }
   GemmArgs g{};
   g.A = gr; g.B = W; g.C = dx;
   g.M = B; g.N = n_in; g.K = n_out; g.lda = n_out; g.ldb = n_out; g.ldc = n_in;
@@ -298,6 +312,8 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
                                     int n_in, int n_out, void *stream) {
   TN_REQUIRE(x && gr && dW && db, TN_ERR_ARG, "tn_dense_bwd_weights: null argument");
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0, TN_ERR_SHAPE, "tn_dense_bwd_weights: bad shape");
+  if (dense_small_ok(n_in, n_out))
+    return dense_bwd_weights_small(x, gr, dW, db, B, n_in, n_out, (cudaStream_t)stream);
   GemmArgs g{};
   g.A = x; g.B = gr; g.C = dW;
   g.M = n_in; g.N = n_out; g.K = B; g.lda = n_in; g.ldb = n_out; g.ldc = n_out;
@@ -306,7 +322,7 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_gemm<1, 0, 2>(g, vec, "tn_dense_bwd_weights", st);
   if (rc) return rc;
-  colsum_kernel<<<ceil_div(n_out, 32), 256, 0, st>>>(gr, db, B, n_out);
+  colsum_kernel<<<ceil_div(n_out, 32), 1024, 0, st>>>(gr, db, B, n_out);
   TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
   return TN_OK;
 }

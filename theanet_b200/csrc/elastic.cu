@@ -86,7 +86,9 @@ __global__ void elastic_field_kernel(tn_elastic_prm prm, const float *__restrict
   }
   __syncthreads();
 
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  // one warp per pixel: lanes split the filter rows, fixed-order shuffle tree combines them
+  const int lane = threadIdx.x & 31;
+  const int pix = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= hw) return;
   const int y = pix / h, x = pix % h;
   double T[2] = {(double)y, (double)x};                                                   // :77
@@ -96,21 +98,25 @@ __global__ void elastic_field_kernel(tn_elastic_prm prm, const float *__restrict
   }
   if (prm.magnitude != 0.f) {                                                             // :85-97
     const int sg = prm.sigma;
+    const int j0 = max(0, sg - x), j1 = min(k, h + sg - x);
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       const float *el = s_el + c * hw;
       double acc = 0.0;
-      for (int i = 0; i < k; ++i) {
+      for (int i = lane; i < k; i += 32) {
         const int yy = y + i - sg;
         if (yy < 0 || yy >= h) continue;
         const float *frow = s_filt + (k - 1 - i) * k;
-        const int j0 = max(0, sg - x), j1 = min(k, h + sg - x);
+        const float *erow = el + yy * h + x - sg;
         for (int j = j0; j < j1; ++j)
-          acc = __dadd_rn(acc, __dmul_rn((double)el[yy * h + x + j - sg], (double)frow[k - 1 - j]));
+          acc = __dadd_rn(acc, __dmul_rn((double)erow[j], (double)frow[k - 1 - j]));
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
       T[c] = __dadd_rn(T[c], (double)(float)acc);
     }
   }
+  if (lane != 0) return;
   if (prm.zoom_on || prm.angle_rad != 0.f) {                                              // :100-118
     T[0] = __dsub_rn(T[0], sc.origin[0]);
     T[1] = __dsub_rn(T[1], sc.origin[1]);
@@ -266,8 +272,8 @@ extern "C" int tn_elastic_field(const tn_elastic_prm *prm, const float *noise, c
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     TN_REQUIRE(e == cudaSuccess, TN_ERR_CUDA, "tn_elastic_field: %s", cudaGetErrorString(e));
   }
-  const int threads = 64;  // many small blocks: the 961-tap loops are latency-bound
-  elastic_field_kernel<<<ceil_div(hw, threads), threads, smem, (cudaStream_t)stream>>>(
+  const int threads = 256;  // 8 warps = 8 pixels per CTA
+  elastic_field_kernel<<<ceil_div(hw, threads / 32), threads, smem, (cudaStream_t)stream>>>(
       *prm, noise, u_inj, filt, seed, ctl, target, tyx, gidx, gfrac);
   TN_LAUNCH_CHECK("tn_elastic_field");
   return TN_OK;
