@@ -145,6 +145,10 @@ int tn_dense_bwd_data(const float *g, const float *W, float *dx, int B, int n_in
 /* dW = x^T.g, db = column sums of g */
 int tn_dense_bwd_weights(const float *x, const float *g, float *dW, float *db, int B, int n_in,
                          int n_out, void *stream);
+/* Dense-path selector (process-wide debugging / benchmarking knob): 0 = auto (tcgen05 tensor cores
+ * with 3xTF32 error compensation whenever n_in, n_out are multiples of 4 and n_out > 32, CUDA-core
+ * kernels otherwise), 1 = CUDA cores only, 2 = tensor cores with a single TF32 pass, 3 = as 0. */
+int tn_set_dense_mode(int mode);
 /* standalone dropout / test-time scaling: out = x * mask * scale (also used on gradients) */
 int tn_dropout_apply(const float *x, float *out, int B, int n, double pkeep, uint64_t seed,
                      const int32_t *ctl, const float *mask_inj, float scale, void *stream);

@@ -10,6 +10,7 @@
 // tensor-core input rounding; the bf16 config uses the tcgen05 path (gemm_tc.cu).
 #include "common.cuh"
 #include "dense_small.cuh"
+#include "dense_tc.cuh"
 
 namespace tn {
 
@@ -242,6 +243,12 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const float *__restrict__ 
 
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 
+int g_dense_mode = 0;
+static bool use_tc(int n_in, int n_out, const void *a, const void *b, const void *c) {
+  return g_dense_mode != 1 && dense_tc_ok(n_in, n_out, a, b, c);
+}
+static int tc_split() { return g_dense_mode == 2 ? 0 : 1; }
+
 template <int AMODE, int BMODE, int EPI>
 static int launch_gemm(const GemmArgs &g, bool vec, const char *name, cudaStream_t st) {
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
@@ -272,6 +279,10 @@ extern "C" int tn_dense_fwd(const float *x, const float *W, const float *bias, f
                 mask_mode(pkeep, mask_inj), act, (float)act_nn, out_scale, B, n_in, n_out};
     return dense_fwd_small(a, (cudaStream_t)stream);
   }
+  if (use_tc(n_in, n_out, x, W, out))
+    return dense_tc_fwd(x, W, bias, out, B, n_in, n_out, act, (float)act_nn,
+                        mask_mode(pkeep, mask_inj), bernoulli_threshold(pkeep), seed, ctl,
+                        mask_inj, out_scale, tc_split(), (cudaStream_t)stream);
   GemmArgs g{};
   g.A = x; g.B = W; g.C = out;
   g.M = B; g.N = n_out; g.K = n_in; g.lda = n_in; g.ldb = n_out; g.ldc = n_out;
@@ -296,6 +307,13 @@ extern "C" int tn_dense_bwd_data(const float *gr, const float *W, float *dx, int
                 bernoulli_threshold(pkeep_prev), mo, act_prev, (float)nn_prev, 1.f, B, n_in, n_out};
     return dense_bwd_data_small(a, (cudaStream_t)stream);
   }
+  if (use_tc(n_in, n_out, gr, W, dx)) {
+    const int mo = prev_out ? mask_mode(pkeep_prev, mask_inj_prev) : 0;
+    TN_REQUIRE(mo != 1 || ctl, TN_ERR_ARG, "tn_dense_bwd_data: dropout needs ctl");
+    return dense_tc_bwd_data(gr, W, dx, B, n_in, n_out, prev_out, act_prev, (float)nn_prev, mo,
+                             bernoulli_threshold(pkeep_prev), seed_prev, ctl, mask_inj_prev,
+                             tc_split(), (cudaStream_t)stream);
+  }
   GemmArgs g{};
   g.A = gr; g.B = W; g.C = dx;
   g.M = B; g.N = n_in; g.K = n_out; g.lda = n_out; g.ldb = n_out; g.ldc = n_in;
@@ -314,6 +332,14 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0, TN_ERR_SHAPE, "tn_dense_bwd_weights: bad shape");
   if (dense_small_ok(n_in, n_out))
     return dense_bwd_weights_small(x, gr, dW, db, B, n_in, n_out, (cudaStream_t)stream);
+  if (use_tc(n_in, n_out, x, gr, dW)) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = dense_tc_bwd_weights(x, gr, dW, B, n_in, n_out, tc_split(), st);
+    if (rc) return rc;
+    colsum_kernel<<<ceil_div(n_out, 32), 1024, 0, st>>>(gr, db, B, n_out);
+    TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
+    return TN_OK;
+  }
   GemmArgs g{};
   g.A = x; g.B = gr; g.C = dW;
   g.M = n_in; g.N = n_out; g.K = B; g.lda = n_in; g.ldb = n_out; g.ldc = n_out;
@@ -324,5 +350,11 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
   if (rc) return rc;
   colsum_kernel<<<ceil_div(n_out, 32), 1024, 0, st>>>(gr, db, B, n_out);
   TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
+  return TN_OK;
+}
+
+extern "C" int tn_set_dense_mode(int mode) {
+  TN_REQUIRE(mode >= 0 && mode <= 3, TN_ERR_ARG, "tn_set_dense_mode: mode must be 0..3");
+  g_dense_mode = mode;
   return TN_OK;
 }

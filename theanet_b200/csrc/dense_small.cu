@@ -81,7 +81,10 @@ __global__ void __launch_bounds__(256) dense_bwd_data_small_kernel(SmallArgs a) 
   const bool vec = (a.n_in & 3) == 0;
   for (int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; b < a.B; b += warps) {
     const float gv = lane < a.n_out ? a.x[(size_t)b * a.n_out + lane] : 0.f;
-    for (int q = lane; q < nquads; q += 32) {
+    // warp-uniform trip count: every lane takes part in the shuffles, idle lanes redo the last quad
+    for (int qb = 0; qb < nquads; qb += 32) {
+      const bool live = qb + lane < nquads;
+      const int q = live ? qb + lane : nquads - 1;
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int j = 0; j < a.n_out; ++j) {
         const float gj = __shfl_sync(0xffffffffu, gv, j);
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(256) dense_bwd_data_small_kernel(SmallArgs a) 
           }
         }
       }
+      if (!live) continue;
       float *o = a.out + (size_t)b * a.n_in + i0;
       if (vec) {
         *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
