@@ -120,6 +120,28 @@ size_t tn_conv2d_wgrad_workspace_bytes(int B, int C, int S, int M, int f);
 int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float *db, void *workspace, int B,
                     int C, int S, int M, int f, int pad_lo, int out_sz, void *stream);
 
+/* ---- ConvLayer + PoolLayer fused (small channel counts: theanet's shipped networks) ----------
+ * One image per CTA stays resident in shared memory; f must be 3 or 5.  pool = 0: no PoolLayer
+ * follows (pooled / pool_out_sz ignored; dtop is dL/da).  Replaces nnet.conv2d + pool_2d
+ * (convpool.py:54-56,106-107) and their gradients (tt.grad, layer.py:83). */
+/* a = act(conv(x) + b) (B,M,out,out); pooled = maxpool(a) (B,M,pool_out,pool_out) */
+int tn_convpool_fprop(const float *x, const float *W, const float *bias, float *a, float *pooled,
+                      int B, int C, int S, int M, int f, int pad_lo, int out_sz, int act,
+                      int act_nn, int pool, int pool_out_sz, void *stream);
+size_t tn_convpool_bwd_weights_workspace_bytes(int B, int C, int M, int f);
+/* dW, db from (x, a, pooled, dtop = dL/dpooled): dL/dz = [a == pooled(window)] * dtop * act'(a)
+ * is rebuilt in shared memory (every tied maximum receives the gradient) */
+int tn_convpool_bwd_weights(const float *x, const float *a, const float *pooled,
+                            const float *dtop, float *dW, float *db, void *workspace, int B,
+                            int C, int S, int M, int f, int pad_lo, int out_sz, int act,
+                            int act_nn, int pool, int pool_out_sz, void *stream);
+/* dx = dL/d(layer input); if below != NULL (the output of a ConvLayer feeding this one directly)
+ * dx is multiplied by that layer's act' */
+int tn_convpool_bwd_data(const float *a, const float *pooled, const float *dtop, const float *W,
+                         float *dx, const float *below, int B, int C, int S, int M, int f,
+                         int pad_lo, int out_sz, int act, int act_nn, int pool, int pool_out_sz,
+                         int act_below, int nn_below, void *stream);
+
 /* ---- PoolLayer (theanet/layer/convpool.py:97-127; pool_2d max, stride = window) ------------- */
 /* planes = B*C; out_sz = ceil(S/p) (ignore_border=False) or S/p */
 int tn_maxpool_fwd(const float *x, float *out, int planes, int S, int p, int out_sz,

@@ -219,6 +219,80 @@ def test_conv_fprop_dgrad_wgrad(C, case):
     assert rel(dbd.cpu().numpy(), db) < 1e-5
 
 
+# --------------------------------------------------------------------------------------------
+FUSED_CASES = [  # B, C, S, M, f, mode, act, pool, ignore_border
+    (6, 1, 28, 4, 3, 'valid', 'relu10', 2, False),      # mnist.prms conv 1
+    (6, 4, 13, 20, 3, 'valid', 'relu05', 2, False),     # mnist.prms conv 2 (edge windows 1 wide)
+    (3, 3, 12, 7, 3, 'same', 'relu05', 3, False),
+    (3, 2, 11, 5, 5, 'valid', 'tanh', 2, True),
+    (2, 5, 14, 9, 5, 'same', 'relu', 2, False),
+    (700, 4, 13, 20, 3, 'valid', 'relu05', 2, False),   # more images than CTAs
+    (2, 1, 64, 4, 3, 'valid', 'relu10', 2, False),      # C5 geometry
+]
+
+
+@pytest.mark.parametrize('case', range(len(FUSED_CASES)))
+def test_convpool_fused_fwd_bwd(C, case):
+    B, Cin, S, M, f, mode, actn, p, ib = FUSED_CASES[case]
+    rng = np.random.default_rng(260 + case)
+    # quantised inputs and weights make exact ties inside pool windows likely
+    x = (rng.integers(-3, 4, (B, Cin, S, S)) / 4).astype(np.float32)
+    W = (rng.integers(-2, 3, (M, Cin, f, f)) / 4).astype(np.float32)
+    b = ((2 * rng.integers(-2, 3, M) + 1) / 32).astype(np.float32)   # z is never exactly 0 (A5)
+    pad_lo, out_sz = O.conv_geometry(S, f, mode)
+    z, cache = O.conv_forward(x, W, mode)
+    a = O.act_forward(actn, z + b[None, :, None, None])
+    pooled, pcache = O.pool_forward(a, p, ib)
+    P = pooled.shape[-1]
+    act, nn = C.act_code(actn)
+    xd, Wd, bd = dev(x), dev(W), dev(b)
+    ad = torch.zeros((B, M, out_sz, out_sz), device='cuda')
+    pd = torch.zeros((B, M, P, P), device='cuda')
+    C.call('tn_convpool_fprop', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(ad), C.ptr(pd), B, Cin, S, M,
+           f, pad_lo, out_sz, act, nn, p, P, None)
+    sync()
+    assert rel(ad.cpu().numpy(), a) < 1e-6
+    assert np.array_equal(pd.cpu().numpy(), O.pool_forward(ad.cpu().numpy(), p, ib)[0])  # bit-exact
+    # backward from the oracle's own activations so that the tie pattern is identical
+    ad, pd = dev(a), dev(pooled)
+    dtop = rng.standard_normal(pooled.shape).astype(np.float32)
+    da = O.pool_backward(dtop, pcache)
+    gz = O.act_backward(actn, z + b[None, :, None, None], a, da)
+    dW, db, dx = O.conv_backward(gz, W, cache)
+    nb = C.lib.tn_convpool_bwd_weights_workspace_bytes(B, Cin, M, f)
+    ws = torch.zeros(nb // 4 + 1, device='cuda')
+    dtd = dev(dtop)
+    res = []
+    for _ in range(2):
+        dWd, dbd = torch.zeros_like(Wd), torch.zeros_like(bd)
+        C.call('tn_convpool_bwd_weights', C.ptr(xd), C.ptr(ad), C.ptr(pd), C.ptr(dtd), C.ptr(dWd),
+               C.ptr(dbd), C.ptr(ws), B, Cin, S, M, f, pad_lo, out_sz, act, nn, p, P, None)
+        sync()
+        res.append((dWd.cpu().numpy(), dbd.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    tol = 1e-5 if B < 100 else 1e-4
+    assert rel(res[0][0], dW) < tol and rel(res[0][1], db) < tol
+    dxd = torch.zeros_like(xd)
+    C.call('tn_convpool_bwd_data', C.ptr(ad), C.ptr(pd), C.ptr(dtd), C.ptr(Wd), C.ptr(dxd), None, B,
+           Cin, S, M, f, pad_lo, out_sz, act, nn, p, P, 0, 0, None)
+    sync()
+    assert rel(dxd.cpu().numpy(), dx) < 1e-5
+    C.call('tn_convpool_bwd_data', C.ptr(ad), C.ptr(pd), C.ptr(dtd), C.ptr(Wd), C.ptr(dxd),
+           C.ptr(xd), B, Cin, S, M, f, pad_lo, out_sz, act, nn, p, P, *C.act_code('relu07'), None)
+    sync()
+    xnz = np.where(x == 0, 1.0, x).astype(np.float32)    # off the kink (assumption A5)
+    want = O.act_backward('relu07', xnz, xnz, dx)
+    got = dxd.cpu().numpy()
+    assert rel(got[x != 0], want[x != 0]) < 1e-5
+
+
+def test_convpool_fused_refuses_unsupported(C):
+    x = torch.zeros((1, 2, 9, 9), device='cuda')
+    rc = C.lib.tn_convpool_fprop(C.ptr(x), C.ptr(x), C.ptr(x), C.ptr(x), C.ptr(x), 1, 2, 9, 4, 4, 0,
+                                 6, 0, 0, 2, 3, None)
+    assert rc == -5 and 'filter_sz' in C.last_error()
+
+
 def test_conv_wgrad_many_images_is_deterministic(C):
     B, Cin, S, M, f = 700, 4, 13, 20, 3          # more images than CTAs: grid-stride + 2 stages
     rng = np.random.default_rng(5)

@@ -95,7 +95,7 @@ class DistContext:
 
 class NeuralNet():
     def __init__(self, layers, training_params, allwts=None, test_x=None, device=None, dist=None,
-                 use_graph=True):
+                 use_graph=True, fuse_conv=True):
         if allwts is None:
             self.rand_gen = np.random.RandomState(training_params['SEED'])
         else:
@@ -114,6 +114,7 @@ class NeuralNet():
             device = 'cuda' if torch.cuda.is_available() else 'cpu'
         self.device = torch.device(device)
         self.use_graph = use_graph and self.device.type == 'cuda'
+        self.fuse_conv = fuse_conv
 
         # Input Layer
         input_layer_type = getattr(layer, layers[0][0])
@@ -269,12 +270,19 @@ class NeuralNet():
             prm.nearest = int(bool(l0.nearest))
             prm.clip_hi = h - 1 - .001
             self.el_prm = prm
-        # workspaces
+        # workspaces; conv_fused[li]: ConvLayer li (+ the PoolLayer right above it) runs on the
+        # fused small-channel kernels (conv_fused.cu)
         self.ws = {}
+        self.conv_fused = {}
         for li, lyr in enumerate(self.tr_layers):
             if isinstance(lyr, ConvLayer):
                 nb = _C.lib.tn_conv2d_wgrad_workspace_bytes(B, lyr.num_prev_maps, lyr.in_sz,
                                                             lyr.num_maps, lyr.filter_sz)
+                nxt = self.tr_layers[li + 1] if li + 1 < len(self.tr_layers) else None
+                if self.fuse_conv and isinstance(nxt, PoolLayer) and self._fused_conv_ok(lyr):
+                    self.conv_fused[li] = nxt
+                    nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
+                        B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
                 self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
         nb = _C.lib.tn_update_workspace_bytes(max(1, self.n_segs), total)
         self.ws_update = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
@@ -282,6 +290,21 @@ class NeuralNet():
         self.launches = {}          # 'train' / 'test' -> kernels of this library per step
         if self.dist.world > 1:     # replicas must start identical (rank 0 wins)
             torch.distributed.broadcast(self.theta, src=0, group=self.dist.group)
+
+    @staticmethod
+    def _fused_conv_ok(lyr):
+        """Limits of the fused conv(+pool) kernels (conv_fused.cu: fill_geom and shared memory)."""
+        f, C_, M, S, O = lyr.filter_sz, lyr.num_prev_maps, lyr.num_maps, lyr.in_sz, lyr.out_sz
+        G, CG = (M + 3) // 4, (C_ + 3) // 4
+        if f not in (3, 5) or G * C_ * f > 256 or M * O * O >= 65536 or C_ * S * S >= 65536:
+            return False
+        strips_o, strips_s = (O + 3) // 4, (S + 3) // 4
+        ng = max(1, min(256 // max(1, CG * S * strips_s), M))
+        smem = 4 * max(
+            C_ * f * f * 4 * G + C_ * (O + f - 1) * (strips_o * 4 + f - 1) + M * O * O,
+            C_ * (O + f - 1) ** 2 + 4 * G * O * O,
+            M * f * f * 4 * CG + M * (S + f - 1) * (strips_s * 4 + f - 1) + ng * 4 * CG * S * S)
+        return smem <= 96 * 1024
 
     # ------------------------------------------------------------------------------------------
     # launch helpers
@@ -332,10 +355,18 @@ class NeuralNet():
                 _C.call('tn_elastic_warp', _C.ptr(corpus), idxp, ctl, B, C_, h, invert, mode, gidx,
                         gfrac, pflip, self._inj(0, 'flip') if train else None, seed, _C.ptr(out),
                         st)
+            elif isinstance(lyr, ConvLayer) and li in self.conv_fused:
+                pl = self.conv_fused[li]
+                _C.call('tn_convpool_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor),
+                        _C.ptr(lyr.b.tensor), _C.ptr(out), _C.ptr(self.out[li + 1]), B,
+                        lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
+                        lyr.out_sz, lyr.act.code, lyr.act.nn, pl.pool_sz, pl.out_sz, st)
             elif isinstance(lyr, ConvLayer):
                 _C.call('tn_conv2d_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor), _C.ptr(lyr.b.tensor),
                         _C.ptr(out), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz,
                         lyr.pad_lo, lyr.out_sz, lyr.act.code, lyr.act.nn, st)
+            elif isinstance(lyr, PoolLayer) and (li - 1) in self.conv_fused:
+                pass                                  # produced by the fused conv kernel below it
             elif isinstance(lyr, PoolLayer):
                 _C.call('tn_maxpool_fwd', _C.ptr(x), _C.ptr(out), B * lyr.num_maps, lyr.in_sz,
                         lyr.pool_sz, lyr.out_sz, st)
@@ -390,6 +421,22 @@ class NeuralNet():
                     po, ac, nn, pk, sd, mi = fuse or (None, 0, 0, 1.0, 0, None)
                     _C.call('tn_dense_bwd_data', _C.ptr(g), _C.ptr(lyr.w.tensor), _C.ptr(dx), B,
                             lyr.n_in, lyr.n_out, _C.ptr(po), ac, nn, pk, sd, ctl, mi, st)
+            elif isinstance(lyr, ConvLayer) and li in self.conv_fused:
+                # g is dL/d(pooled output); the pool backward is folded into both kernels
+                pl = self.conv_fused[li]
+                geom = (B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
+                        lyr.out_sz, lyr.act.code, lyr.act.nn, pl.pool_sz, pl.out_sz)
+                if self.trainable[li]:
+                    _C.call('tn_convpool_bwd_weights', _C.ptr(x), _C.ptr(self.out[li]),
+                            _C.ptr(self.out[li + 1]), _C.ptr(g), _C.ptr(lyr.W.grad),
+                            _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), *geom, st)
+                if below:
+                    if fuse and fuse[3] < 1.0:
+                        raise NotImplementedError("dropout-masked dense output feeding a conv")
+                    po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, 0, 0)
+                    _C.call('tn_convpool_bwd_data', _C.ptr(self.out[li]), _C.ptr(self.out[li + 1]),
+                            _C.ptr(g), _C.ptr(lyr.W.tensor), _C.ptr(dx), _C.ptr(po), *geom, ac, nn,
+                            st)
             elif isinstance(lyr, ConvLayer):
                 if self.trainable[li]:
                     _C.call('tn_conv2d_wgrad', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.W.grad),
@@ -402,6 +449,8 @@ class NeuralNet():
                             lyr.filter_sz, lyr.pad_lo, lyr.out_sz, ac, nn, st)
                     if fuse and fuse[3] < 1.0:
                         raise NotImplementedError("dropout-masked dense output feeding a conv")
+            elif isinstance(lyr, PoolLayer) and (li - 1) in self.conv_fused:
+                continue                              # g stays dL/d(pooled): see the conv branch
             elif isinstance(lyr, PoolLayer):
                 if below:
                     ac, nn = (fuse[1], fuse[2]) if fuse else (_C.ACT_LINEAR, 0)
