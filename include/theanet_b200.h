@@ -190,6 +190,23 @@ int tn_softmax_test_stats(const float *z, const int32_t *y, const int32_t *idx,
                           const int32_t *ctl, int B, int n, float *logprob, int64_t *preds,
                           float *stats, void *stream);
 
+/* ---- classifier head: HiddenLayer -> SoftmaxLayer with n_in <= 1024, n_out <= 32, fused ---------
+ * (hidden.py:30-32 + outlayers.py:50-51,83-102 and their gradients in two launches) */
+int tn_softmax_head_supported(int n_in, int n_out);
+/* scores = h.W + b; logprob, g, rowloss as tn_softmax_nll_fwd_bwd; dh = g.W^T (may be NULL) and,
+ * if below != 0, dh *= mask_below * act_below'(h): dL/dz of the layer that produced h */
+int tn_softmax_head_fwd_bwd(const float *h, const float *W, const float *bias, const int32_t *y,
+                            const int32_t *idx, const int32_t *ctl, int B, int n_in, int n_out,
+                            float inv_global_batch, float *logprob, float *g, float *rowloss,
+                            float *dh, int below, int act_below, int nn_below,
+                            double pkeep_below, uint64_t seed_below, const float *mask_inj_below,
+                            void *stream);
+size_t tn_softmax_head_workspace_bytes(int B, int n_in, int n_out);
+/* dW = h^T.g, db = column sums of g.  `workspace` must be zero-filled ONCE by the caller before
+ * the first call (it holds the completion tickets, which every launch leaves at zero). */
+int tn_softmax_head_bwd_weights(const float *h, const float *g, float *dW, float *db,
+                                void *workspace, int B, int n_in, int n_out, void *stream);
+
 /* ---- Layer.get_updates / get_wtcost (theanet/layer/layer.py:70-117) ------------------------- */
 typedef struct tn_param_seg {
   int64_t offset;   /* element offset into the flat theta / velocity / gradient buffers */

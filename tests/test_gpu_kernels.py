@@ -415,6 +415,70 @@ def test_dense_fwd_bwd(C, case):
     assert rel(dx.cpu().numpy(), want) < 1e-5
 
 
+@pytest.mark.parametrize('B,n_in,n_out,pdrop', [(1024, 500, 10, .5), (20, 500, 10, .5), (33, 36, 11, 0.),
+                                                (17, 1000, 32, .25), (5, 7, 3, 0.), (300, 130, 2, .5)])
+def test_softmax_head_fused(C, B, n_in, n_out, pdrop):
+    rng = np.random.default_rng(B + n_in)
+    seed, step, s0, row0 = 991, 3, 64, 5
+    zprev = rng.standard_normal((B, n_in)).astype(np.float32)
+    pm = philox.bernoulli_mask(seed, philox.PURPOSE_DROPOUT, step, np.arange(s0, s0 + B), n_in,
+                               1 - pdrop) if pdrop else np.ones((B, n_in), np.float32)
+    prev_a = O.act_forward('relu01', zprev)
+    h = (prev_a * pm).astype(np.float32)                  # stored masked output of the layer below
+    W = (rng.standard_normal((n_in, n_out)) / np.sqrt(n_in)).astype(np.float32)
+    b = rng.standard_normal(n_out).astype(np.float32)
+    y = rng.integers(0, n_out, B + row0).astype(np.int32)
+    yb = y[row0:row0 + B]
+    ctl = make_ctl(C, step=step, sample0=s0, row0=row0)
+    inv = 1.0 / (2 * B)
+    z = h.astype(np.float64) @ W.astype(np.float64) + b
+    lp = O.log_softmax(z)
+    g = np.exp(lp)
+    g[np.arange(B), yb] -= 1
+    g *= inv
+    dh = O.act_backward('relu01', zprev, prev_a, (g @ W.astype(np.float64).T) * pm)
+    hd, Wd, bd, yd = dev(h), dev(W), dev(b), dev(y)
+    lpd = torch.zeros((B, n_out), device='cuda')
+    gd = torch.zeros((B, n_out), device='cuda')
+    rl = torch.zeros(B, device='cuda')
+    dhd = torch.full((B, n_in), -7.0, device='cuda')
+    assert C.lib.tn_softmax_head_supported(n_in, n_out)
+    C.call('tn_softmax_head_fwd_bwd', C.ptr(hd), C.ptr(Wd), C.ptr(bd), C.ptr(yd), None, C.ptr(ctl),
+           B, n_in, n_out, inv, C.ptr(lpd), C.ptr(gd), C.ptr(rl), C.ptr(dhd), 1,
+           *C.act_code('relu01'), 1 - pdrop, seed, None, None)
+    sync()
+    assert rel(lpd.cpu().numpy(), lp) < 1e-5
+    assert rel(gd.cpu().numpy(), g) < 1e-5
+    assert rel(rl.cpu().numpy(), -lp[np.arange(B), yb]) < 1e-5
+    assert rel(dhd.cpu().numpy(), dh) < 1e-5
+    # plain dh (nothing fused below) and index-list labels
+    idx = rng.permutation(B + row0)[:B].astype(np.int32)
+    C.call('tn_softmax_head_fwd_bwd', C.ptr(hd), C.ptr(Wd), C.ptr(bd), C.ptr(yd), C.ptr(dev(idx)),
+           C.ptr(ctl), B, n_in, n_out, inv, C.ptr(lpd), C.ptr(gd), C.ptr(rl), C.ptr(dhd), 0, 0, 0,
+           1.0, 0, None, None)
+    sync()
+    g2 = np.exp(lp)
+    g2[np.arange(B), y[idx]] -= 1
+    g2 *= inv
+    assert rel(gd.cpu().numpy(), g2) < 1e-5
+    assert rel(dhd.cpu().numpy(), g2 @ W.astype(np.float64).T) < 1e-5
+    # weights: twice through the same workspace (tickets must return to zero), bit-identical
+    nb = C.lib.tn_softmax_head_workspace_bytes(B, n_in, n_out)
+    ws = torch.zeros(nb // 4 + 1, device='cuda')
+    gd = dev(g.astype(np.float32))
+    res = []
+    for _ in range(2):
+        dW, db = torch.zeros_like(Wd), torch.zeros_like(bd)
+        C.call('tn_softmax_head_bwd_weights', C.ptr(hd), C.ptr(gd), C.ptr(dW), C.ptr(db), C.ptr(ws),
+               B, n_in, n_out, None)
+        sync()
+        res.append((dW.cpu().numpy(), db.cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    g32 = g.astype(np.float32).astype(np.float64)
+    assert rel(res[0][0], h.astype(np.float64).T @ g32) < 1e-5
+    assert rel(res[0][1], g32.sum(0)) < 1e-5
+
+
 def test_dropout_apply_and_act_bwd(C):
     rng = np.random.default_rng(9)
     B, n = 9, 1001

@@ -44,25 +44,69 @@ struct FusedArgs {
   int B, C, S, M, f, pad_lo, O, P, pool;  // pool = window (0: none)
   int act, act_below;
   float nn, nn_below;
-  FastDiv divO, divOO, divP, divPP, divS, divpool;
+  float s_neg, s_zero;  // leaky-ReLU slopes for a < 0 and a == 0 (act_bwd_from_out, hoisted)
+  FastDiv divO, divOO, divP, divPP, divS, divSp, divstrO, divstrS;
 };
 
-// dL/dz of one element of a (see header comment)
-__device__ __forceinline__ float grad_z(const FusedArgs &k, const float *__restrict__ a_img,
-                                        const float *__restrict__ pooled_img,
-                                        const float *__restrict__ dtop_img, int m, int i, int j) {
-  const float av = a_img[(m * k.O + i) * k.O + j];
-  float g;
+// act'(a) from the stored output with the leaky-ReLU slopes precomputed on the host
+__device__ __forceinline__ float act_bwd_k(const FusedArgs &k, float a) {
+  if (k.act == TN_ACT_LEAKY) return a > 0.f ? 1.f : (a < 0.f ? k.s_neg : k.s_zero);
+  return act_bwd_from_out(a, k.act, k.nn);
+}
+
+// gs[(m*ldm + i + pd)*ldw + j + pd] = dL/dz of image element (m, i, j) (see header comment).  With
+// a pool layer the loop runs over pooled cells (coalesced reads of pooled / dtop, index math
+// amortised over the window); elements outside every window (ignore_border) are never written, so
+// gs must have been zero-filled once.
+__device__ __forceinline__ void stage_gz(const FusedArgs &k, const float *__restrict__ a_img,
+                                         const float *__restrict__ p_img,
+                                         const float *__restrict__ d_img, float *gs, int ldm,
+                                         int ldw, int pd) {
+  const int tid = threadIdx.x;
   if (k.pool) {
-    const int oi = (int)k.divpool.div(i), oj = (int)k.divpool.div(j);
-    if (oi >= k.P || oj >= k.P) return 0.f;
-    const int o = (m * k.P + oi) * k.P + oj;
-    if (av != pooled_img[o]) return 0.f;
-    g = dtop_img[o];
+    const int PP = k.P * k.P;
+    for (int t = tid; t < k.M * PP; t += kFT) {
+      const int m = (int)k.divPP.div(t);
+      const int p = t - m * PP;
+      const int oi = (int)k.divP.div(p), oj = p - oi * k.P;
+      const float po = p_img[t], d = d_img[t];
+      const int y0 = oi * k.pool, x0 = oj * k.pool;
+      const int y1 = min(y0 + k.pool, k.O), x1 = min(x0 + k.pool, k.O);
+      for (int yy = y0; yy < y1; ++yy) {
+        const float *ar = a_img + (m * k.O + yy) * k.O;
+        float *gr = gs + (m * ldm + yy + pd) * ldw + pd;
+        for (int xx = x0; xx < x1; ++xx) {
+          const float av = ar[xx];
+          gr[xx] = av == po ? d * act_bwd_k(k, av) : 0.f;
+        }
+      }
+    }
   } else {
-    g = dtop_img[(m * k.O + i) * k.O + j];
+    const int OO = k.O * k.O;
+    for (int t = tid; t < k.M * OO; t += kFT) {
+      const int m = (int)k.divOO.div(t);
+      const int p = t - m * OO;
+      const int i = (int)k.divO.div(p), j = p - i * k.O;
+      gs[(m * ldm + i + pd) * ldw + j + pd] = d_img[t] * act_bwd_k(k, a_img[t]);
+    }
   }
-  return g * act_bwd_from_out(av, k.act, k.nn);
+}
+
+// xs[(c*Sp + Y)*ldw + X] = x[c, Y - pad, X - pad] or 0: one padded row per warp pass
+__device__ __forceinline__ void stage_x(const FusedArgs &k, const float *__restrict__ img,
+                                        float *xs, int Sp, int ldw) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int row = warp; row < k.C * Sp; row += kFT / 32) {
+    const int c = (int)k.divSp.div(row);
+    const int y = row - c * Sp - k.pad_lo;
+    const bool yok = y >= 0 && y < k.S;
+    const float *src = img + (c * k.S + y) * k.S - k.pad_lo;
+    float *dst = xs + row * ldw;
+    for (int X = lane; X < ldw; X += 32) {
+      const int x = X - k.pad_lo;
+      dst[X] = (yok && x >= 0 && x < k.S) ? src[X] : 0.f;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -89,28 +133,19 @@ __global__ void __launch_bounds__(kFT) convpool_fprop_kernel(const FusedArgs k) 
     const int c = r / F;
     ws[t] = co < k.M ? k.W[((co * k.C + c) * F + (F - 1 - u)) * F + (F - 1 - v)] : 0.f;
   }
-  const int nX = k.C * Sp * Wp;
   const int OO = k.O * k.O;
   const bool vec_a = (((size_t)k.M * OO) & 3) == 0;
 
   for (int b = blockIdx.x; b < k.B; b += gridDim.x) {
-    const float *img = k.x + (size_t)b * k.C * k.S * k.S;
-    for (int t = tid; t < nX; t += kFT) {
-      const int X = t % Wp;
-      int r = t / Wp;
-      const int Y = r % Sp;
-      const int c = r / Sp;
-      const int y = Y - k.pad_lo, x = X - k.pad_lo;
-      xs[t] = (y >= 0 && y < k.S && x >= 0 && x < k.S) ? img[(c * k.S + y) * k.S + x] : 0.f;
-    }
+    stage_x(k, k.x + (size_t)b * k.C * k.S * k.S, xs, Sp, Wp);
     __syncthreads();
     // items: (channel group g, output row i, strip s)
     const int items = G * k.O * strips;
     for (int it = tid; it < items; it += kFT) {
-      const int s = it % strips;
-      int r = it / strips;
-      const int i = r % k.O;
-      const int g = r / k.O;
+      const int r = (int)k.divstrO.div(it);
+      const int s = it - r * strips;
+      const int g = (int)k.divO.div(r);
+      const int i = r - g * k.O;
       const int j0 = s * kL;
       float acc[kL][4];
 #pragma unroll
@@ -203,28 +238,14 @@ __global__ void __launch_bounds__(kFT) convpool_wgrad_kernel(const FusedArgs k) 
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int v = 0; v < F; ++v) acc[q][v] = 0.f;
-  for (int t = k.M * OO + tid; t < mP * OO; t += kFT) gs[t] = 0.f;  // padded maps stay zero
+  for (int t = tid; t < mP * OO; t += kFT) gs[t] = 0.f;  // padded maps / uncovered borders stay 0
+  __syncthreads();
 
   const int PP = k.P * k.P;
   for (int b = blockIdx.x; b < k.B; b += gridDim.x) {
-    const float *img = k.x + (size_t)b * k.C * k.S * k.S;
-    for (int t = tid; t < k.C * Sp * Sp; t += kFT) {
-      const int X = t % Sp;
-      int r = t / Sp;
-      const int Y = r % Sp;
-      const int ci = r / Sp;
-      const int y = Y - k.pad_lo, x = X - k.pad_lo;
-      xs[t] = (y >= 0 && y < k.S && x >= 0 && x < k.S) ? img[(ci * k.S + y) * k.S + x] : 0.f;
-    }
-    const float *a_img = k.a + (size_t)b * k.M * OO;
-    const float *p_img = k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr;
-    const float *d_img = k.dtop + (size_t)b * k.M * (k.pool ? PP : OO);
-    for (int t = tid; t < k.M * OO; t += kFT) {
-      const int m = (int)k.divOO.div(t);
-      const int p = t - m * OO;
-      const int i = (int)k.divO.div(p), j = p - i * k.O;
-      gs[t] = grad_z(k, a_img, p_img, d_img, m, i, j);
-    }
+    stage_x(k, k.x + (size_t)b * k.C * k.S * k.S, xs, Sp, Sp);
+    stage_gz(k, k.a + (size_t)b * k.M * OO, k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr,
+             k.dtop + (size_t)b * k.M * (k.pool ? PP : OO), gs, k.O, k.O, 0);
     __syncthreads();
     if (active) {
       for (int i = slice; i < k.O; i += nsl) {
@@ -349,22 +370,16 @@ __global__ void __launch_bounds__(kFT) convpool_dgrad_kernel(const FusedArgs k, 
   const int items = NG * CG * k.S * strips;
 
   for (int b = blockIdx.x; b < k.B; b += gridDim.x) {
-    const float *a_img = k.a + (size_t)b * k.M * OO;
-    const float *p_img = k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr;
-    const float *d_img = k.dtop + (size_t)b * k.M * (k.pool ? PP : OO);
-    for (int t = tid; t < k.M * OO; t += kFT) {
-      const int m = (int)k.divOO.div(t);
-      const int p = t - m * OO;
-      const int i = (int)k.divO.div(p), j = p - i * k.O;
-      gs[(m * Hp + i + pd) * Wg + j + pd] = grad_z(k, a_img, p_img, d_img, m, i, j);
-    }
+    stage_gz(k, k.a + (size_t)b * k.M * OO, k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr,
+             k.dtop + (size_t)b * k.M * (k.pool ? PP : OO), gs, Hp, Wg, pd);
     __syncthreads();
     for (int it = tid; it < items; it += kFT) {
-      const int s = it % strips;
-      int r = it / strips;
-      const int y = r % k.S; r /= k.S;
-      const int cg = r % CG;
-      const int mg = r / CG;
+      int r = (int)k.divstrS.div(it);
+      const int s = it - r * strips;
+      const int r2 = (int)k.divS.div(r);
+      const int y = r - r2 * k.S;
+      const int cg = r2 % CG;
+      const int mg = r2 / CG;
       const int x0 = s * kL;
       float acc[kL][4];
 #pragma unroll
@@ -405,7 +420,7 @@ __global__ void __launch_bounds__(kFT) convpool_dgrad_kernel(const FusedArgs k, 
     for (int t = tid; t < k.C * SS; t += kFT) {
       float s = 0.f;
       for (int mg = 0; mg < NG; ++mg) s += part[mg * cP * SS + t];
-      if (bl_img) s *= act_bwd_from_out(bl_img[t], k.act_below, k.nn_below);
+      if (bl_img) s *= act_bwd_from_out(bl_img[t], k.act_below, k.nn_below);  // rare: conv on conv
       dx_img[t] = s;
     }
     __syncthreads();
@@ -431,6 +446,14 @@ static int set_smem(K kernel, size_t smem, const char *who) {
   return TN_OK;
 }
 
+static void set_act(FusedArgs &k, int act, int act_nn) {
+  k.act = act;
+  k.nn = (float)act_nn;
+  const float sl = (float)act_nn / 100.f;           // as act_bwd_from_out
+  k.s_neg = act_nn == 0 ? 0.f : sl;
+  k.s_zero = act_nn == 0 ? 0.f : 1.f + sl;
+}
+
 static int fill_geom(FusedArgs &k, int B, int C, int S, int M, int f, int pad_lo, int O, int pool,
                      int P, const char *who) {
   TN_REQUIRE(B > 0 && C > 0 && S > 0 && M > 0 && O > 0 && pad_lo >= 0 && pad_lo <= f - 1 &&
@@ -445,7 +468,8 @@ static int fill_geom(FusedArgs &k, int B, int C, int S, int M, int f, int pad_lo
   k.pool = pool;
   k.divO = FastDiv(O); k.divOO = FastDiv(O * O); k.divS = FastDiv(S);
   k.divP = FastDiv(pool ? P : 1); k.divPP = FastDiv(pool ? P * P : 1);
-  k.divpool = FastDiv(pool ? pool : 1);
+  k.divSp = FastDiv(O + f - 1);
+  k.divstrO = FastDiv(ceil_div(O, kL)); k.divstrS = FastDiv(ceil_div(S, kL));
   TN_REQUIRE((int64_t)M * O * O < 65536 && (int64_t)C * S * S < 65536, TN_ERR_UNSUPPORTED,
              "%s: image too large for the fused small-channel path", who);
   return TN_OK;
@@ -464,7 +488,8 @@ extern "C" int tn_convpool_fprop(const float *x, const float *W, const float *bi
   FusedArgs k{};
   int rc = fill_geom(k, B, C, S, M, f, pad_lo, out_sz, pool, pool_out_sz, who);
   if (rc) return rc;
-  k.x = x; k.W = W; k.bias = bias; k.a = a; k.pooled = pooled; k.act = act; k.nn = (float)act_nn;
+  k.x = x; k.W = W; k.bias = bias; k.a = a; k.pooled = pooled;
+  set_act(k, act, act_nn);
   const int G = (M + 3) / 4, strips = ceil_div(out_sz, kL);
   const size_t smem = ((size_t)C * f * f * 4 * G + (size_t)C * (out_sz + f - 1) * (strips * kL + f - 1) + 3 +
                        (size_t)M * out_sz * out_sz) * sizeof(float);
@@ -496,7 +521,8 @@ extern "C" int tn_convpool_bwd_weights(const float *x, const float *a, const flo
   TN_REQUIRE(G * C * f <= kFT, TN_ERR_UNSUPPORTED,
              "%s: ceil(M/4)*C*f = %d exceeds %d threads; use the general path", who, G * C * f, kFT);
   k.x = x; k.a = const_cast<float *>(a); k.pooled = const_cast<float *>(pooled); k.dtop = dtop;
-  k.partial = (float *)workspace; k.act = act; k.nn = (float)act_nn;
+  k.partial = (float *)workspace;
+  set_act(k, act, act_nn);
   const int Sp = out_sz + f - 1;
   size_t smem = ((size_t)C * Sp * Sp + (size_t)mP * out_sz * out_sz) * sizeof(float);
   const int T = G * C * f, nsl = std::max(1, std::min(kFT / T, out_sz));
@@ -526,7 +552,8 @@ extern "C" int tn_convpool_bwd_data(const float *a, const float *pooled, const f
   int rc = fill_geom(k, B, C, S, M, f, pad_lo, out_sz, pool, pool_out_sz, who);
   if (rc) return rc;
   k.a = const_cast<float *>(a); k.pooled = const_cast<float *>(pooled); k.dtop = dtop; k.W = W;
-  k.dx = dx; k.below = below; k.act = act; k.nn = (float)act_nn; k.act_below = act_below;
+  k.dx = dx; k.below = below; k.act_below = act_below;
+  set_act(k, act, act_nn);
   k.nn_below = (float)nn_below;
   const int CG = (C + 3) / 4, cP = 4 * CG, strips = ceil_div(S, kL);
   int NG = kFT / std::max(1, CG * S * strips);

@@ -95,7 +95,7 @@ class DistContext:
 
 class NeuralNet():
     def __init__(self, layers, training_params, allwts=None, test_x=None, device=None, dist=None,
-                 use_graph=True, fuse_conv=True):
+                 use_graph=True, fuse_conv=True, fuse_head=True):
         if allwts is None:
             self.rand_gen = np.random.RandomState(training_params['SEED'])
         else:
@@ -115,6 +115,7 @@ class NeuralNet():
         self.device = torch.device(device)
         self.use_graph = use_graph and self.device.type == 'cuda'
         self.fuse_conv = fuse_conv
+        self.fuse_head = fuse_head
 
         # Input Layer
         input_layer_type = getattr(layer, layers[0][0])
@@ -284,6 +285,12 @@ class NeuralNet():
                     nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
                         B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
                 self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
+        # classifier head (narrow SoftmaxLayer) on the fused kernels of head.cu
+        self.head = bool(self.fuse_head and self.trainable[-1] and
+                         _C.lib.tn_softmax_head_supported(last.n_in, last.n_out))
+        if self.head:
+            nb = _C.lib.tn_softmax_head_workspace_bytes(B, last.n_in, last.n_out)
+            self.ws_head = torch.zeros((nb + 3) // 4, dtype=f32, device=dev)   # tickets start at 0
         nb = _C.lib.tn_update_workspace_bytes(max(1, self.n_segs), total)
         self.ws_update = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
         self._graphs = {}
@@ -326,6 +333,8 @@ class NeuralNet():
         ctl = _C.ptr(self.ctl)
         idxp = _C.ptr(idx)
         for li, lyr in enumerate(layers):
+            if train and self.head and li == len(layers) - 1:
+                break                                 # scores are computed by the fused head
             out = self.out[li]
             x = self.out[li - 1] if li else None
             if isinstance(lyr, (InputLayer, ElasticLayer)):
@@ -413,7 +422,11 @@ class NeuralNet():
             below = self.need_below[li]
             dx = self.dbuf[li - 1]
             fuse = self._fuse_info(li - 1) if below else None
-            if isinstance(lyr, HiddenLayer):
+            if self.head and li == len(L) - 1:
+                # dL/dz of the layer below was already produced by tn_softmax_head_fwd_bwd
+                _C.call('tn_softmax_head_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
+                        _C.ptr(lyr.b.grad), _C.ptr(self.ws_head), B, lyr.n_in, lyr.n_out, st)
+            elif isinstance(lyr, HiddenLayer):
                 if self.trainable[li]:
                     _C.call('tn_dense_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
                             _C.ptr(lyr.b.grad), B, lyr.n_in, lyr.n_out, st)
@@ -492,10 +505,23 @@ class NeuralNet():
         if idx is not None:
             self.idx.copy_(self.idx_host, non_blocking=True)
         self._forward(self.tr_layers, True, corpus, idx, labels)
-        n_out = self.tr_layers[-1].n_out
-        _C.call('tn_softmax_nll_fwd_bwd', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
-                _C.ptr(self.ctl), B, n_out, 1.0 / self.batch_sz, _C.ptr(self.logprob),
-                _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
+        last = self.tr_layers[-1]
+        n_out = last.n_out
+        if self.head:
+            li = len(self.tr_layers) - 1
+            below = self.need_below[li]
+            fuse = self._fuse_info(li - 1) if below else None
+            po, ac, nn, pk, sd, mi = fuse or (None, 0, 0, 1.0, 0, None)
+            _C.call('tn_softmax_head_fwd_bwd', _C.ptr(self.out[li - 1]), _C.ptr(last.w.tensor),
+                    _C.ptr(last.b.tensor), _C.ptr(labels), _C.ptr(idx), _C.ptr(self.ctl), B,
+                    last.n_in, n_out, 1.0 / self.batch_sz, _C.ptr(self.logprob),
+                    _C.ptr(self.gsoft), _C.ptr(self.rowloss),
+                    _C.ptr(self.dbuf[li - 1]) if below else None, int(fuse is not None), ac, nn,
+                    pk, sd, mi, st)
+        else:
+            _C.call('tn_softmax_nll_fwd_bwd', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
+                    _C.ptr(self.ctl), B, n_out, 1.0 / self.batch_sz, _C.ptr(self.logprob),
+                    _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
         self._backward()
         _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
         self.dist.all_reduce_sum(self.grad)          # the one collective of the step
