@@ -21,6 +21,8 @@
 // ONE 32-deep k-block (two buffers, ping-pong): the same warps pull each finished block into
 // float32 registers with round-to-nearest adds ("promotion"), which brings the result to within
 // CUDA-core SGEMM accuracy (~3e-7).
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -31,9 +33,11 @@ namespace tn {
 using namespace tc;
 
 constexpr int TC_BM = 128;       // accumulator rows = TMEM lanes
-constexpr int TC_BK = 32;        // fp32 elements per 128-byte swizzle row
+constexpr int TC_KA = 2;         // 128-byte swizzle rows (32 fp32) per operand row and stage
+constexpr int TC_BK = 32 * TC_KA;  // k-block depth: the fixed cost of a pipeline stage (mbarrier
+                                   // round trip, ~0.35 us measured) is amortised over 64-deep blocks
 constexpr int TC_THREADS = 192;  // 6 warps
-constexpr int TC_A_BYTES = TC_BM * 128;
+constexpr int TC_A_BYTES = TC_BM * 128 * TC_KA;
 
 struct TcArgs {
   float *C;
@@ -50,9 +54,10 @@ struct TcArgs {
 
 template <int BN, int SPLIT>
 struct TcCfg {
-  static constexpr int B_BYTES = BN * 128;
+  static constexpr int B_BYTES = BN * 128 * TC_KA;
   static constexpr int STAGE_BYTES = (TC_A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = (STAGE_BYTES * 6 <= 200 * 1024) ? 6 : (STAGE_BYTES * 4 <= 200 * 1024 ? 4 : 3);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 1 ? 1 : STAGES_RAW);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = (SPLIT ? 2 : 1) * (BN < 32 ? 32 : BN);  // power of two
 };
@@ -113,19 +118,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(empty(s), ph ^ 1u);
         mbar_expect_tx(full(s), TC_A_BYTES + Cfg::B_BYTES);
         const int k0 = kb * TC_BK;
-        if (!g.a_mn) {
-          tma_load_2d(stA(s), &tmA, full(s), k0, m0);
-        } else {
+        if (!g.a_mn) {   // K-major: one (32 x 128 rows) box per 128-byte k-atom
+#pragma unroll
+          for (int a = 0; a < TC_KA; ++a)
+            tma_load_2d(stA(s) + a * (TC_BM * 128), &tmA, full(s), k0 + 32 * a, m0);
+        } else {         // M-major: one (32 wide x BK deep) box per 32-row column block
 #pragma unroll
           for (int j = 0; j < TC_BM / 32; ++j)
-            tma_load_2d(stA(s) + j * 4096, &tmA, full(s), m0 + 32 * j, k0);
+            tma_load_2d(stA(s) + j * (TC_BK * 128), &tmA, full(s), m0 + 32 * j, k0);
         }
         if (!g.b_mn) {
-          tma_load_2d(stB(s), &tmB, full(s), k0, n0);
+#pragma unroll
+          for (int a = 0; a < TC_KA; ++a)
+            tma_load_2d(stB(s) + a * (BN * 128), &tmB, full(s), k0 + 32 * a, n0);
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 32; ++j)
-            tma_load_2d(stB(s) + j * 4096, &tmB, full(s), n0 + 32 * j, k0);
+            tma_load_2d(stB(s) + j * (TC_BK * 128), &tmB, full(s), n0 + 32 * j, k0);
         }
       }
     }
@@ -134,8 +143,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       const uint32_t idesc = make_idesc(KIND_TF32, g.a_mn, g.b_mn, TC_BM, BN);
       // per 8-deep k-step: K-major advances 32 B inside the swizzle row, MN-major one 1 KB group
-      const uint32_t a_step = g.a_mn ? 1024u : 32u, b_step = g.b_mn ? 1024u : 32u;
-      const uint32_t a_lbo = g.a_mn ? 4096u : 16u, b_lbo = g.b_mn ? 4096u : 16u;
+      const uint32_t a_lbo = g.a_mn ? TC_BK * 128u : 16u, b_lbo = g.b_mn ? TC_BK * 128u : 16u;
+      // byte offset of 8-deep k-step j inside a stage tile
+      auto a_off = [&](int j) -> uint32_t {
+        return g.a_mn ? 1024u * j : (uint32_t)((j >> 2) * (TC_BM * 128) + (j & 3) * 32);
+      };
+      auto b_off = [&](int j) -> uint32_t {
+        return g.b_mn ? 1024u * j : (uint32_t)((j >> 2) * (BN * 128) + (j & 3) * 32);
+      };
       // MN-major tf32 tiles use the 32-byte-atom swizzle (4-row atoms), K-major the plain one
       const uint32_t a_sbo = g.a_mn ? 512u : 1024u, b_sbo = g.b_mn ? 512u : 1024u;
       const uint32_t a_lay = g.a_mn ? LAYOUT_SW128_32B : LAYOUT_SW128;
@@ -150,11 +165,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t td = tmem_base + (SPLIT ? (uint32_t)(tb * BN) : 0u);
 #pragma unroll
         for (int j = 0; j < TC_BK / 8; ++j) {
-          const uint64_t ad = make_smem_desc(stA(s) + j * a_step, a_lbo, a_sbo, a_lay);
-          const uint64_t bd = make_smem_desc(stB(s) + j * b_step, b_lbo, b_sbo, b_lay);
+          const uint64_t ad = make_smem_desc(stA(s) + a_off(j), a_lbo, a_sbo, a_lay);
+          const uint64_t bd = make_smem_desc(stB(s) + b_off(j), b_lbo, b_sbo, b_lay);
           if (SPLIT) {
-            const uint64_t al = make_smem_desc(stAlo(s) + j * a_step, a_lbo, a_sbo, a_lay);
-            const uint64_t bl = make_smem_desc(stBlo(s) + j * b_step, b_lbo, b_sbo, b_lay);
+            const uint64_t al = make_smem_desc(stAlo(s) + a_off(j), a_lbo, a_sbo, a_lay);
+            const uint64_t bl = make_smem_desc(stBlo(s) + b_off(j), b_lbo, b_sbo, b_lay);
             umma<KIND_TF32>(td, al, bd, idesc, j ? 1u : 0u);   // every k-block starts from zero
             umma<KIND_TF32>(td, ad, bl, idesc, 1u);
             umma<KIND_TF32>(td, ad, bd, idesc, 1u);
@@ -371,19 +386,23 @@ static int gemm_tc(const float *A, int lda, int a_mn, const float *B, int ldb, i
   const int mt = ceil_div(g.M, TC_BM);
   int BN = 128;
   while (BN > 32 && mt * ceil_div(g.N, BN) < 96) BN >>= 1;
+  if (const char *e = getenv("TN_TC_BN")) {  // tuning knob: force the tile width (32, 64, 128)
+    const int v = atoi(e);
+    if (v == 32 || v == 64 || v == 128) BN = v;
+  }
+  if (split && BN > 64) BN = 64;   // hi + lo copies of a 128-wide stage would leave one stage
   CUtensorMap tmA, tmB;
   int rc;
-  if (!a_mn) rc = tc_make_map_2d(&tmA, A, g.M, g.K, lda, TC_BK, TC_BM, 0, who);
+  if (!a_mn) rc = tc_make_map_2d(&tmA, A, g.M, g.K, lda, 32, TC_BM, 0, who);
   else rc = tc_make_map_2d(&tmA, A, g.K, g.M, lda, 32, TC_BK, 1, who);
   if (rc) return rc;
-  if (!b_mn) rc = tc_make_map_2d(&tmB, B, g.N, g.K, ldb, TC_BK, BN, 0, who);
+  if (!b_mn) rc = tc_make_map_2d(&tmB, B, g.N, g.K, ldb, 32, BN, 0, who);
   else rc = tc_make_map_2d(&tmB, B, g.K, g.N, ldb, 32, TC_BK, 1, who);
   if (rc) return rc;
   g.a_mn = a_mn;
   g.b_mn = b_mn;
   if (split) {
     switch (BN) {
-      case 128: return launch_tc<128, 1>(tmA, tmB, g, who, st);
       case 64: return launch_tc<64, 1>(tmA, tmB, g, who, st);
       default: return launch_tc<32, 1>(tmA, tmB, g, who, st);
     }

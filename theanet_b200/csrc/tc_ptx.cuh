@@ -28,12 +28,34 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Spins on try_wait (a hardware-suspended wait); traps after ~2 s so that a protocol bug shows up
-// as a launch failure instead of a hung GPU.
+// Spins until the phase with the given parity has completed; traps after ~2 s so that a protocol
+// bug shows up as a launch failure instead of a hung GPU.  TN_MBAR_MODE: 0 = try_wait (hardware
+// suspended wait, default time limit), 1 = test_wait (pure polling), 2 = try_wait with a short
+// suspend-time hint.
+#ifndef TN_MBAR_MODE
+#define TN_MBAR_MODE 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   const long long t0 = clock64();
   while (true) {
+#if TN_MBAR_MODE == 1
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+#elif TN_MBAR_MODE == 2
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(32u)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -41,9 +63,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(done)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     if (done) break;
     if (clock64() - t0 > 4000000000ll) __trap();
   }
+}
+
+// whole-warp wait with a single polling lane (31 fewer waiters on the barrier unit)
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
 }
 
 // ---- fences --------------------------------------------------------------------------------------
