@@ -23,6 +23,7 @@ import torch
 
 from . import _C
 from . import layer
+from .dist import DistContext
 from .layer import (InputLayer, ElasticLayer, ConvLayer, PoolLayer, DropOutLayer, HiddenLayer,
                     SoftmaxLayer)
 
@@ -75,17 +76,6 @@ def _as_numpy(data):
     if isinstance(data, torch.Tensor):
         return data
     return np.asarray(data)
-
-
-class DistContext:
-    """Data-parallel context: one process per GPU, torch.distributed for the plumbing."""
-
-    def __init__(self, rank=0, world=1, group=None):
-        self.rank, self.world, self.group = rank, world, group
-
-    def all_reduce_sum(self, t):
-        if self.world > 1:
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM, group=self.group)
 
 
 ###############################################################################
