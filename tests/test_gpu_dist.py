@@ -1,0 +1,22 @@
+"""Data-parallel parity on real GPUs (needs >= 2): two ranks over NCCL reproduce the CPU oracle's
+single-process result within 1e-3 (measured ~2e-6), eager and CUDA-graph modes."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('graph', [0, 1])
+def test_two_gpu_data_parallel_matches_oracle(graph):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+           '--master-addr', '127.0.0.1', '--master-port', str(29600 + graph),
+           os.path.join(ROOT, 'tools', 'dp_check.py'), '--graph', str(graph)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT)
+    assert 'DP_CHECK_OK world=2' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

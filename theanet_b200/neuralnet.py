@@ -15,6 +15,7 @@ graph refreshes from pinned host memory.
 PyTorch is used for device memory, streams, CUDA graphs and torch.distributed only.
 """
 import ctypes
+import os
 from functools import reduce
 from operator import mul
 
@@ -106,6 +107,7 @@ class NeuralNet():
         self.use_graph = use_graph and self.device.type == 'cuda'
         self.fuse_conv = fuse_conv
         self.fuse_head = fuse_head
+        self.nccl_in_graph = os.environ.get('TN_GRAPH_NCCL', '0') == '1'
 
         # Input Layer
         input_layer_type = getattr(layer, layers[0][0])
@@ -514,11 +516,29 @@ class NeuralNet():
                     _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
         self._backward()
         _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
+        if self.dist.world > 1 and not self.nccl_in_graph:
+            return                                   # the caller reduces, then _update_launches
         self.dist.all_reduce_sum(self.grad)          # the one collective of the step
+        self._update_launches()
+
+    def _update_launches(self):
         _C.call('tn_sgd_momentum_maxnorm_update', _C.ptr(self.theta), _C.ptr(self.vel),
                 _C.ptr(self.grad), self.segs, self.n_segs, self.n_flat, _C.ptr(self.ctl), 1.0,
                 _C.ptr(self.nll_sum), 1.0 / self.batch_sz, _C.ptr(self.cost),
-                _C.ptr(self.ws_update), st)
+                _C.ptr(self.ws_update), self._stream())
+
+    def _train_step(self, key, corpus, idx, labels):
+        """One training step.  Single GPU: one CUDA graph.  Data parallel: graph (forward +
+        backward) -> NCCL all-reduce of the flat gradient buffer -> graph (update); set
+        TN_GRAPH_NCCL=1 to capture the collective inside a single graph instead."""
+        if self.dist.world > 1 and not self.nccl_in_graph:
+            self._run(('train_pre',) + key[1:], self._train_launches, (corpus, idx, labels))
+            self.dist.all_reduce_sum(self.grad)
+            self._run(('update',), self._update_launches, (), restore=(self.theta, self.vel))
+            self.launches['train'] = self.launches.get('train_pre', 0) + self.launches.get('update', 0)
+        else:
+            self._run(key, self._train_launches, (corpus, idx, labels),
+                      restore=(self.theta, self.vel))
 
     def _test_launches(self, corpus, idx, labels):
         st = self._stream()
@@ -622,7 +642,7 @@ class NeuralNet():
                     yd.copy_(host[1][lo:lo + Bl], non_blocking=True)
                     idx, row0 = None, 0
             self._set_ctl(row0)
-            self._run(key, self._train_launches, (xd, idx, yd), restore=(self.theta, self.vel))
+            self._train_step(key, xd, idx, yd)
             self.step_count += 1
             if lazy:
                 return self.cost, self.logprob, self.logprob
