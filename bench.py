@@ -157,30 +157,55 @@ def run_reference(args):
 # per-entry-point algorithmic work (for the dominant-kernel roofline)
 # ------------------------------------------------------------------------------------------------
 def stage_work(net):
-    """name -> (algorithmic bytes, flops) per launch group for the layers of `net`."""
+    """(entry point, ordinal in call order) -> (algorithmic bytes, flops) of that call for the
+    layers of `net` (every tensor a call must read or write, once)."""
     from theanet_b200.layer import ConvLayer, HiddenLayer, PoolLayer
     B = net.local_bsz
-    w = {}
-    for li, l in enumerate(net.tr_layers):
+    L = net.tr_layers
+    w, count = {}, {}
+
+    def add(name, byts, fl):
+        k = count.get(name, 0)
+        count[name] = k + 1
+        w[(name, k)] = (byts, fl)
+
+    fwd, bwd = [], []
+    for li, l in enumerate(L):
         if isinstance(l, ConvLayer):
             xin = B * l.num_prev_maps * l.in_sz ** 2 * 4
-            yout = B * l.num_maps * l.out_sz ** 2 * 4
+            a = B * l.num_maps * l.out_sz ** 2 * 4
             wt = l.W.size * 4
             fl = 2 * B * l.num_maps * l.out_sz ** 2 * l.num_prev_maps * l.filter_sz ** 2
-            w[('tn_conv2d_fprop', li)] = (xin + yout + wt, fl)
-            w[('tn_conv2d_dgrad', li)] = (xin + yout + wt, fl)
-            w[('tn_conv2d_wgrad', li)] = (xin + yout + wt, fl)
-        elif isinstance(l, PoolLayer):
+            if li in net.conv_fused:
+                p = B * l.num_maps * net.conv_fused[li].out_sz ** 2 * 4
+                fwd.append(('tn_convpool_fprop', xin + a + p + wt, fl))
+                bwd.append((li, [('tn_convpool_bwd_weights', xin + a + 2 * p + wt, fl)] +
+                            ([('tn_convpool_bwd_data', a + 2 * p + wt + xin, fl)]
+                             if net.need_below[li] else [])))
+            else:
+                fwd.append(('tn_conv2d_fprop', xin + a + wt, fl))
+                bwd.append((li, [('tn_conv2d_wgrad', xin + a + wt, fl)] +
+                            ([('tn_conv2d_dgrad', xin + a + wt, fl)] if net.need_below[li] else [])))
+        elif isinstance(l, PoolLayer) and (li - 1) not in net.conv_fused:
             xin = B * l.num_maps * l.in_sz ** 2 * 4
             yout = B * l.num_maps * l.out_sz ** 2 * 4
-            w[('tn_maxpool_fwd', li)] = (xin + yout, 0)
-            w[('tn_maxpool_bwd', li)] = (2 * xin + 2 * yout, 0)
+            fwd.append(('tn_maxpool_fwd', xin + yout, 0))
+            bwd.append((li, [('tn_maxpool_bwd', 2 * xin + 2 * yout, 0)]))
         elif isinstance(l, HiddenLayer):
             a, b_, c = B * l.n_in * 4, l.n_in * l.n_out * 4, B * l.n_out * 4
             fl = 2 * B * l.n_in * l.n_out
-            w[('tn_dense_fwd', li)] = (a + b_ + c, fl)
-            w[('tn_dense_bwd_data', li)] = (2 * a + b_ + c, fl)
-            w[('tn_dense_bwd_weights', li)] = (a + b_ + c, fl)
+            if net.head and li == len(L) - 1:
+                fwd.append(('tn_softmax_head_fwd_bwd', 2 * a + b_ + 3 * c, 2 * fl))
+                bwd.append((li, [('tn_softmax_head_bwd_weights', a + b_ + c, fl)]))
+            else:
+                fwd.append(('tn_dense_fwd', a + b_ + c, fl))
+                bwd.append((li, [('tn_dense_bwd_weights', a + b_ + c, fl)] +
+                            ([('tn_dense_bwd_data', 2 * a + b_ + c, fl)] if net.need_below[li] else [])))
+    for name, byts, fl in fwd:
+        add(name, byts, fl)
+    for li, calls in reversed(bwd):
+        for name, byts, fl in calls:
+            add(name, byts, fl)
     return w
 
 
@@ -309,27 +334,15 @@ def run_ours(args):
         stages = profile_stages(net, fn_prof, nb, reps=10)
         if rank == 0:
             work = stage_work(net)
-            # ordinal -> layer index per entry point, in call order
-            order = {}
-            from theanet_b200.layer import ConvLayer, HiddenLayer, PoolLayer
-            L = net.tr_layers
-            order['tn_conv2d_fprop'] = [i for i, l in enumerate(L) if isinstance(l, ConvLayer)]
-            order['tn_maxpool_fwd'] = [i for i, l in enumerate(L) if isinstance(l, PoolLayer)]
-            order['tn_dense_fwd'] = [i for i, l in enumerate(L) if isinstance(l, HiddenLayer)]
-            order['tn_dense_bwd_weights'] = order['tn_dense_fwd'][::-1]
-            order['tn_dense_bwd_data'] = order['tn_dense_fwd'][::-1]
-            order['tn_conv2d_wgrad'] = order['tn_conv2d_fprop'][::-1]
-            order['tn_conv2d_dgrad'] = order['tn_conv2d_fprop'][::-1][:-1]
-            order['tn_maxpool_bwd'] = order['tn_maxpool_fwd'][::-1]
             total_ms = sum(stages.values())
             (name, k), t_ms = max(stages.items(), key=lambda kv: kv[1])
-            li = order.get(name, [None] * (k + 1))[k] if name in order else None
-            byts, fl = work.get((name, li), (None, None))
+            li = k
+            byts, fl = work.get((name, k), (None, None))
             share = {"{}#{}".format(n_, k_): round(v / total_ms, 4)
                      for (n_, k_), v in sorted(stages.items(), key=lambda kv: -kv[1])[:8]}
             if byts is not None:
                 ach = byts / (t_ms * 1e-3) / 1e9
-                roof = {"bound": "hbm", "kernel": "{} (layer {})".format(name, li),
+                roof = {"bound": "hbm", "kernel": "{} (call #{} of the step)".format(name, li),
                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                         "traffic": None, "launch_ms": t_ms, "algorithmic_bytes": byts,
                         "algorithmic_flops": fl,

@@ -40,11 +40,23 @@ __host__ __device__ inline int64_t min64(int64_t a, int64_t b) { return a < b ? 
 // Activations.  Forward follows layer.py:36 literally (max(0,x) + (min(0,x)*NN)/100, each op
 // rounded in float32) so reluNN is bit-exact against the numpy restatement.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float act_fwd(float z, int act, float nn) {
+// t / 100 correctly rounded without the division unit: q0 = t*RN(1/100), one FMA residual, one FMA
+// correction (Markstein).  Checked exhaustively over whole binades against IEEE division
+// (tools notes in DESIGN.md); exponent extremes fall back to __fdiv_rn.
+__device__ __forceinline__ float div100_rn(float t) {
+  const float q0 = __fmul_rn(t, 0.01f);
+  const float e = __fmaf_rn(-100.f, q0, t);
+  const float q = __fmaf_rn(e, 0.01f, q0);
+  const float at = fabsf(t);
+  if (at > 1e-28f && at < 1e30f) return q;
+  return t == 0.f ? t : __fdiv_rn(t, 100.f);
+}
+
+// The transcendental activations live out of line: inlined into every unrolled epilogue they made
+// the kernels 100-370 KB of SASS, far beyond the 32 KB instruction cache, and the epilogues ran at
+// instruction-fetch speed (DESIGN.md "measured").  ReLU-family and linear stay inline.
+static __device__ __noinline__ float act_fwd_slow(float z, int act) {
   switch (act) {
-    case TN_ACT_LINEAR: return z;
-    case TN_ACT_RELU: return fmaxf(0.f, z);
-    case TN_ACT_LEAKY: return z > 0.f ? z : __fdiv_rn(__fmul_rn(fminf(0.f, z), nn), 100.f);
     case TN_ACT_TANH: return tanhf(z);
     case TN_ACT_SCALED_TANH: return 1.7f * tanhf(__fdiv_rn(2.f * z, 3.f));
     case TN_ACT_SIGMOID: return __fdiv_rn(1.f, 1.f + expf(-z));
@@ -52,20 +64,8 @@ __device__ __forceinline__ float act_fwd(float z, int act, float nn) {
   }
   return z;
 }
-
-// d act / dz expressed through the stored output a = act(z).  For reluNN (NN >= 1) sign(a) ==
-// sign(z), and at exactly 0 Theano's maximum/minimum gradients both fire (slope 1 + NN/100).
-// For relu / relu00 a == 0 stands for every z <= 0 and gets slope 0 (z == 0 exactly is the only
-// deviation from Theano, a measure-zero event).
-__device__ __forceinline__ float act_bwd_from_out(float a, int act, float nn) {
+static __device__ __noinline__ float act_bwd_slow(float a, int act) {
   switch (act) {
-    case TN_ACT_LINEAR: return 1.f;
-    case TN_ACT_RELU: return a > 0.f ? 1.f : 0.f;
-    case TN_ACT_LEAKY: {
-      if (nn == 0.f) return a > 0.f ? 1.f : 0.f;
-      const float s = __fdiv_rn(nn, 100.f);
-      return a > 0.f ? 1.f : (a < 0.f ? s : 1.f + s);
-    }
     case TN_ACT_TANH: return 1.f - a * a;
     case TN_ACT_SCALED_TANH: {
       const float t = __fdiv_rn(a, 1.7f);
@@ -75,6 +75,75 @@ __device__ __forceinline__ float act_bwd_from_out(float a, int act, float nn) {
     case TN_ACT_SOFTPLUS: return 1.f - expf(-a);
   }
   return 1.f;
+}
+
+__device__ __forceinline__ float act_fwd(float z, int act, float nn) {
+  if (act == TN_ACT_LEAKY) return z > 0.f ? z : div100_rn(__fmul_rn(fminf(0.f, z), nn));
+  if (act == TN_ACT_LINEAR) return z;
+  if (act == TN_ACT_RELU) return fmaxf(0.f, z);
+  return act_fwd_slow(z, act);
+}
+
+// d act / dz expressed through the stored output a = act(z).  For reluNN (NN >= 1) sign(a) ==
+// sign(z), and at exactly 0 Theano's maximum/minimum gradients both fire (slope 1 + NN/100).
+// For relu / relu00 a == 0 stands for every z <= 0 and gets slope 0 (z == 0 exactly is the only
+// deviation from Theano, a measure-zero event).
+__device__ __forceinline__ float act_bwd_from_out(float a, int act, float nn) {
+  if (act == TN_ACT_LEAKY) {
+    if (nn == 0.f) return a > 0.f ? 1.f : 0.f;
+    const float s = div100_rn(nn);
+    return a > 0.f ? 1.f : (a < 0.f ? s : 1.f + s);
+  }
+  if (act == TN_ACT_LINEAR) return 1.f;
+  if (act == TN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  return act_bwd_slow(a, act);
+}
+
+// Activation bundle with the leaky-ReLU slopes hoisted to the host: the common case costs a
+// uniform compare instead of the 7-way switch (which nvcc turns into an indirect branch per element).
+struct ActK {
+  int act;
+  float nn, s_neg, s_zero;
+};
+inline ActK make_actk(int act, int act_nn) {
+  ActK k;
+  k.act = act;
+  k.nn = (float)act_nn;
+  const float sl = (float)act_nn / 100.f;
+  k.s_neg = act_nn == 0 ? 0.f : sl;
+  k.s_zero = act_nn == 0 ? 0.f : 1.f + sl;
+  return k;
+}
+inline bool act_is_fast(int act) {
+  return act == TN_ACT_LEAKY || act == TN_ACT_LINEAR || act == TN_ACT_RELU;
+}
+// GEN = false: the kernel is only launched with ReLU-family / linear activations and contains no
+// call at all (a possible call in a hot kernel costs registers even when it is never taken)
+template <bool GEN>
+__device__ __forceinline__ float act_fwd_t(const ActK &k, float z) {
+  if (k.act == TN_ACT_LEAKY) return z > 0.f ? z : div100_rn(__fmul_rn(z, k.nn));
+  if (k.act == TN_ACT_LINEAR) return z;
+  if (!GEN || k.act == TN_ACT_RELU) return fmaxf(0.f, z);
+  return act_fwd_slow(z, k.act);
+}
+template <bool GEN>
+__device__ __forceinline__ float act_bwd_t(const ActK &k, float a) {
+  if (k.act == TN_ACT_LEAKY) return a > 0.f ? 1.f : (a < 0.f ? k.s_neg : k.s_zero);
+  if (k.act == TN_ACT_LINEAR) return 1.f;
+  if (!GEN || k.act == TN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  return act_bwd_slow(a, k.act);
+}
+__device__ __forceinline__ float act_fwd_k(const ActK &k, float z) {
+  if (k.act == TN_ACT_LEAKY) return z > 0.f ? z : div100_rn(__fmul_rn(z, k.nn));
+  if (k.act == TN_ACT_LINEAR) return z;
+  if (k.act == TN_ACT_RELU) return fmaxf(0.f, z);
+  return act_fwd_slow(z, k.act);
+}
+__device__ __forceinline__ float act_bwd_k(const ActK &k, float a) {
+  if (k.act == TN_ACT_LEAKY) return a > 0.f ? 1.f : (a < 0.f ? k.s_neg : k.s_zero);
+  if (k.act == TN_ACT_LINEAR) return 1.f;
+  if (k.act == TN_ACT_RELU) return a > 0.f ? 1.f : 0.f;
+  return act_bwd_slow(a, k.act);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -44,20 +44,15 @@ struct FusedArgs {
   int B, C, S, M, f, pad_lo, O, P, pool;  // pool = window (0: none)
   int act, act_below;
   float nn, nn_below;
-  float s_neg, s_zero;  // leaky-ReLU slopes for a < 0 and a == 0 (act_bwd_from_out, hoisted)
+  ActK ak, akb;         // activation of this layer / of the conv below, leaky slopes hoisted
   FastDiv divO, divOO, divP, divPP, divS, divSp, divstrO, divstrS;
 };
-
-// act'(a) from the stored output with the leaky-ReLU slopes precomputed on the host
-__device__ __forceinline__ float act_bwd_k(const FusedArgs &k, float a) {
-  if (k.act == TN_ACT_LEAKY) return a > 0.f ? 1.f : (a < 0.f ? k.s_neg : k.s_zero);
-  return act_bwd_from_out(a, k.act, k.nn);
-}
 
 // gs[(m*ldm + i + pd)*ldw + j + pd] = dL/dz of image element (m, i, j) (see header comment).  With
 // a pool layer the loop runs over pooled cells (coalesced reads of pooled / dtop, index math
 // amortised over the window); elements outside every window (ignore_border) are never written, so
 // gs must have been zero-filled once.
+template <bool GEN>
 __device__ __forceinline__ void stage_gz(const FusedArgs &k, const float *__restrict__ a_img,
                                          const float *__restrict__ p_img,
                                          const float *__restrict__ d_img, float *gs, int ldm,
@@ -77,7 +72,7 @@ __device__ __forceinline__ void stage_gz(const FusedArgs &k, const float *__rest
         float *gr = gs + (m * ldm + yy + pd) * ldw + pd;
         for (int xx = x0; xx < x1; ++xx) {
           const float av = ar[xx];
-          gr[xx] = av == po ? d * act_bwd_k(k, av) : 0.f;
+          gr[xx] = av == po ? d * act_bwd_t<GEN>(k.ak, av) : 0.f;
         }
       }
     }
@@ -87,7 +82,7 @@ __device__ __forceinline__ void stage_gz(const FusedArgs &k, const float *__rest
       const int m = (int)k.divOO.div(t);
       const int p = t - m * OO;
       const int i = (int)k.divO.div(p), j = p - i * k.O;
-      gs[(m * ldm + i + pd) * ldw + j + pd] = d_img[t] * act_bwd_k(k, a_img[t]);
+      gs[(m * ldm + i + pd) * ldw + j + pd] = d_img[t] * act_bwd_t<GEN>(k.ak, a_img[t]);
     }
   }
 }
@@ -113,7 +108,7 @@ __device__ __forceinline__ void stage_x(const FusedArgs &k, const float *__restr
 // forward: conv + bias + activation (+ max-pool)
 // ---------------------------------------------------------------------------------------------
 // smem: ws[(c*F+u)*F+v][coP] | xs[C][Sp][Wp] (zero padded) | as[M][O][O]
-template <int F>
+template <int F, bool GEN>
 __global__ void __launch_bounds__(kFT) convpool_fprop_kernel(const FusedArgs k) {
   extern __shared__ __align__(16) float sm[];
   const int G = (k.M + 3) >> 2, coP = 4 * G;
@@ -180,7 +175,7 @@ __global__ void __launch_bounds__(kFT) convpool_fprop_kernel(const FusedArgs k) 
           const float bm = k.bias[m];
 #pragma unroll
           for (int l = 0; l < kL; ++l)
-            if (j0 + l < k.O) as[(m * k.O + i) * k.O + j0 + l] = act_fwd(acc[l][q] + bm, k.act, k.nn);
+            if (j0 + l < k.O) as[(m * k.O + i) * k.O + j0 + l] = act_fwd_t<GEN>(k.ak, acc[l][q] + bm);
         }
       }
     }
@@ -218,7 +213,7 @@ __global__ void __launch_bounds__(kFT) convpool_fprop_kernel(const FusedArgs k) 
 // ---------------------------------------------------------------------------------------------
 // thread = (slice, mg, c, u): 4 maps x F filter columns in registers, sliding window along a row
 // smem: xs[C][Sp][Wx] | gs[mP][O][O]   (aliased by the slice reduction at the end)
-template <int F>
+template <int F, bool GEN>
 __global__ void __launch_bounds__(kFT) convpool_wgrad_kernel(const FusedArgs k) {
   extern __shared__ __align__(16) float sm[];
   const int G = (k.M + 3) >> 2, mP = 4 * G;
@@ -244,7 +239,7 @@ __global__ void __launch_bounds__(kFT) convpool_wgrad_kernel(const FusedArgs k) 
   const int PP = k.P * k.P;
   for (int b = blockIdx.x; b < k.B; b += gridDim.x) {
     stage_x(k, k.x + (size_t)b * k.C * k.S * k.S, xs, Sp, Sp);
-    stage_gz(k, k.a + (size_t)b * k.M * OO, k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr,
+    stage_gz<GEN>(k, k.a + (size_t)b * k.M * OO, k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr,
              k.dtop + (size_t)b * k.M * (k.pool ? PP : OO), gs, k.O, k.O, 0);
     __syncthreads();
     if (active) {
@@ -343,7 +338,7 @@ fused_wgrad_finish_kernel(const float *__restrict__ partial, int nblk, int C, in
 // thread = (map group mg of NG, channel group cg, row y, strip): partial over its maps, 4 input
 // channels x 4 pixels in registers; partials combined through smem in a fixed order
 // smem: ws[(m*F+u)*F+v][cP] | gs[M][Hp][Wg] zero-bordered | part[NG][cP][S][S]
-template <int F>
+template <int F, bool GEN>
 __global__ void __launch_bounds__(kFT) convpool_dgrad_kernel(const FusedArgs k, int NG) {
   extern __shared__ __align__(16) float sm[];
   const int CG = (k.C + 3) >> 2, cP = 4 * CG;
@@ -370,7 +365,7 @@ __global__ void __launch_bounds__(kFT) convpool_dgrad_kernel(const FusedArgs k, 
   const int items = NG * CG * k.S * strips;
 
   for (int b = blockIdx.x; b < k.B; b += gridDim.x) {
-    stage_gz(k, k.a + (size_t)b * k.M * OO, k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr,
+    stage_gz<GEN>(k, k.a + (size_t)b * k.M * OO, k.pool ? k.pooled + (size_t)b * k.M * PP : nullptr,
              k.dtop + (size_t)b * k.M * (k.pool ? PP : OO), gs, Hp, Wg, pd);
     __syncthreads();
     for (int it = tid; it < items; it += kFT) {
@@ -420,7 +415,7 @@ __global__ void __launch_bounds__(kFT) convpool_dgrad_kernel(const FusedArgs k, 
     for (int t = tid; t < k.C * SS; t += kFT) {
       float s = 0.f;
       for (int mg = 0; mg < NG; ++mg) s += part[mg * cP * SS + t];
-      if (bl_img) s *= act_bwd_from_out(bl_img[t], k.act_below, k.nn_below);  // rare: conv on conv
+      if (bl_img) s *= act_bwd_t<GEN>(k.akb, bl_img[t]);  // rare: conv on conv
       dx_img[t] = s;
     }
     __syncthreads();
@@ -449,9 +444,7 @@ static int set_smem(K kernel, size_t smem, const char *who) {
 static void set_act(FusedArgs &k, int act, int act_nn) {
   k.act = act;
   k.nn = (float)act_nn;
-  const float sl = (float)act_nn / 100.f;           // as act_bwd_from_out
-  k.s_neg = act_nn == 0 ? 0.f : sl;
-  k.s_zero = act_nn == 0 ? 0.f : 1.f + sl;
+  k.ak = make_actk(act, act_nn);
 }
 
 static int fill_geom(FusedArgs &k, int B, int C, int S, int M, int f, int pad_lo, int O, int pool,
@@ -493,7 +486,9 @@ extern "C" int tn_convpool_fprop(const float *x, const float *W, const float *bi
   const int G = (M + 3) / 4, strips = ceil_div(out_sz, kL);
   const size_t smem = ((size_t)C * f * f * 4 * G + (size_t)C * (out_sz + f - 1) * (strips * kL + f - 1) + 3 +
                        (size_t)M * out_sz * out_sz) * sizeof(float);
-  void (*kern)(FusedArgs) = f == 3 ? convpool_fprop_kernel<3> : convpool_fprop_kernel<5>;
+  const bool gen = !act_is_fast(act);
+  void (*kern)(FusedArgs) = f == 3 ? (gen ? convpool_fprop_kernel<3, true> : convpool_fprop_kernel<3, false>)
+                                    : (gen ? convpool_fprop_kernel<5, true> : convpool_fprop_kernel<5, false>);
   rc = set_smem(kern, smem, who);
   if (rc) return rc;
   kern<<<images_grid(B), kFT, smem, (cudaStream_t)stream>>>(k);
@@ -527,7 +522,9 @@ extern "C" int tn_convpool_bwd_weights(const float *x, const float *a, const flo
   size_t smem = ((size_t)C * Sp * Sp + (size_t)mP * out_sz * out_sz) * sizeof(float);
   const int T = G * C * f, nsl = std::max(1, std::min(kFT / T, out_sz));
   smem = std::max(smem, (size_t)nsl * T * 4 * f * sizeof(float));
-  void (*kern)(FusedArgs) = f == 3 ? convpool_wgrad_kernel<3> : convpool_wgrad_kernel<5>;
+  const bool gen = !act_is_fast(act);
+  void (*kern)(FusedArgs) = f == 3 ? (gen ? convpool_wgrad_kernel<3, true> : convpool_wgrad_kernel<3, false>)
+                                    : (gen ? convpool_wgrad_kernel<5, true> : convpool_wgrad_kernel<5, false>);
   rc = set_smem(kern, smem, who);
   if (rc) return rc;
   const int grid = images_grid(B);
@@ -553,6 +550,7 @@ extern "C" int tn_convpool_bwd_data(const float *a, const float *pooled, const f
   if (rc) return rc;
   k.a = const_cast<float *>(a); k.pooled = const_cast<float *>(pooled); k.dtop = dtop; k.W = W;
   k.dx = dx; k.below = below; k.act_below = act_below;
+  k.akb = make_actk(act_below, nn_below);
   set_act(k, act, act_nn);
   k.nn_below = (float)nn_below;
   const int CG = (C + 3) / 4, cP = 4 * CG, strips = ceil_div(S, kL);
@@ -560,7 +558,9 @@ extern "C" int tn_convpool_bwd_data(const float *a, const float *pooled, const f
   NG = std::max(1, std::min(NG, M));
   const size_t smem = ((size_t)M * f * f * cP + (size_t)M * (S + f - 1) * (strips * kL + f - 1) +
                        (size_t)NG * cP * S * S) * sizeof(float);
-  void (*kern)(FusedArgs, int) = f == 3 ? convpool_dgrad_kernel<3> : convpool_dgrad_kernel<5>;
+  const bool gen = !act_is_fast(act) || (below && !act_is_fast(act_below));
+  void (*kern)(FusedArgs, int) = f == 3 ? (gen ? convpool_dgrad_kernel<3, true> : convpool_dgrad_kernel<3, false>)
+                                         : (gen ? convpool_dgrad_kernel<5, true> : convpool_dgrad_kernel<5, false>);
   rc = set_smem(kern, smem, who);
   if (rc) return rc;
   kern<<<images_grid(B), kFT, smem, (cudaStream_t)stream>>>(k, NG);

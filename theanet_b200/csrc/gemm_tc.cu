@@ -2,11 +2,11 @@
 // tt.dot and its two gradients via tt.grad, layer.py:83).
 //
 // One warp-specialised kernel serves out = x.W, dx = g.W^T and dW = x^T.g:
-//   warp 0      : TMA producer  -- cp.async.bulk.tensor tiles (128-byte swizzle) into a ring of
-//                 shared-memory stages, completion on mbarriers;
-//   warp 1      : allocates TMEM, one lane issues tcgen05.mma (kind::tf32, fp32 accumulate in
+//   warps 0..3  : TMA producers -- cp.async.bulk.tensor tiles (128-byte swizzle) into a ring of
+//                 shared-memory stages, completion on mbarriers; k-blocks round-robin;
+//   warp 8      : allocates TMEM, one lane issues tcgen05.mma (kind::tf32, fp32 accumulate in
 //                 TMEM) and hands stages back with tcgen05.commit;
-//   warps 2..5  : epilogue -- tcgen05.ld the 128 x BN accumulator, fuse bias / activation /
+//   warps 4..7  : epilogue -- tcgen05.ld the 128 x BN accumulator, fuse bias / activation /
 //                 Philox dropout mask (forward) or mask * act' (backward-data), store fp32.
 // Operands are consumed in the layout theanet's .pkl exposes (row-major x (B, n_in), W (n_in,
 // n_out)): whichever of M/N/K is contiguous in memory, the tile is described to the tensor core as
@@ -36,7 +36,11 @@ constexpr int TC_BM = 128;       // accumulator rows = TMEM lanes
 constexpr int TC_KA = 2;         // 128-byte swizzle rows (32 fp32) per operand row and stage
 constexpr int TC_BK = 32 * TC_KA;  // k-block depth: the fixed cost of a pipeline stage (mbarrier
                                    // round trip, ~0.35 us measured) is amortised over 64-deep blocks
-constexpr int TC_THREADS = 192;  // 6 warps
+constexpr int TC_PROD = 4;       // TMA producer warps (warps 0..3), k-blocks round-robin: a warp
+                                 // gets one mbarrier phase per ~0.36 us (tools/micro/tma_bench2.cu),
+                                 // throughput scales with the number of issuing warps
+constexpr int TC_MMA_WARP = 2 * TC_PROD;           // warps 4..7: epilogue, warp 8: MMA + TMEM
+constexpr int TC_THREADS = 32 * (TC_MMA_WARP + 1);
 constexpr int TC_A_BYTES = TC_BM * 128 * TC_KA;
 
 struct TcArgs {
@@ -48,8 +52,9 @@ struct TcArgs {
   const int32_t *ctl;
   uint64_t seed;
   uint32_t thr;
-  int mask_on, act;
-  float act_nn, scale;
+  int mask_on;
+  ActK ak;
+  float scale;
 };
 
 template <int BN, int SPLIT>
@@ -59,8 +64,62 @@ struct TcCfg {
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 1 ? 1 : STAGES_RAW);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = (SPLIT ? 2 : 1) * (BN < 32 ? 32 : BN);  // power of two
+  // Back-to-back tcgen05.mma on ONE accumulator are serialised by the accumulate dependency
+  // (~112 cycles each whatever N <= 128 is; tools/micro/mma_bench.cu).  The MMAs of a k-block are
+  // therefore dealt round-robin to NACC independent accumulators that the epilogue warps add up.
+  static constexpr int NACC = BN <= 64 ? 4 : 2;
+  static constexpr int TMEM_COLS = (SPLIT ? 2 : 1) * NACC * BN;  // power of two, <= 512
 };
+
+// Epilogue of 4 consecutive columns n..n+3 of row m: dropout mask, bias + activation (forward) or
+// mask * act' (backward-data), store.  Out of line on purpose: unrolled into every 16-column
+// chunk it made the kernel several times larger than the 32 KB instruction cache.
+static __device__ __noinline__ void tc_epi_quad(const TcArgs &g, int m, int n, float v0, float v1,
+                                                float v2, float v3, uint32_t step,
+                                                uint32_t sample0) {
+  float v[4] = {v0, v1, v2, v3};
+  float mk[4] = {1.f, 1.f, 1.f, 1.f};
+  if (g.epi != 2) {
+    if (g.mask_on == 1) {
+      const Philox4 pr = philox_block(g.seed, TN_RNG_DROPOUT, step, sample0 + (uint32_t)m,
+                                      (uint32_t)(n >> 2));
+      mk[0] = pr.x < g.thr ? 1.f : 0.f;
+      mk[1] = pr.y < g.thr ? 1.f : 0.f;
+      mk[2] = pr.z < g.thr ? 1.f : 0.f;
+      mk[3] = pr.w < g.thr ? 1.f : 0.f;
+    } else if (g.mask_on == 2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < g.N) mk[j] = g.mask_inj[(size_t)m * g.N + n + j];
+    }
+  }
+  if (g.epi == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j < g.N) {
+        const float a = act_fwd_k(g.ak, v[j] + g.bias[n + j]);
+        v[j] = g.mask_on ? a * mk[j] : a;
+        if (g.scale != 1.f) v[j] *= g.scale;
+      }
+    }
+  } else if (g.epi == 1 && g.aux) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n + j < g.N) {
+        const float d = act_bwd_k(g.ak, g.aux[(size_t)m * g.N + n + j]);
+        v[j] = (g.mask_on ? v[j] * mk[j] : v[j]) * d;
+      }
+    }
+  }
+  float *c = g.C + (size_t)m * g.ldc + n;
+  if (n + 3 < g.N) {
+    *reinterpret_cast<float4 *>(c) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (n + j < g.N) c[j] = v[j];
+  }
+}
 
 template <int BN, int SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -68,6 +127,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const TcArgs g) {
   using Cfg = TcCfg<BN, SPLIT>;
   constexpr int S = Cfg::STAGES;
+  constexpr int NACC = Cfg::NACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar0 = base + S * Cfg::STAGE_BYTES;  // full[S], xf[S], empty[S], accum, tmem slot
@@ -102,18 +162,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tslot, Cfg::TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_alloc(tslot, Cfg::TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
 
-  if (warp == 0) {
-    // ===== TMA producer =====
+  if (warp < TC_PROD) {
+    // ===== TMA producers =====
     if (lane == 0) {
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
+        // a stage belongs to ONE producer warp, so its phases are waited on in order (a warp
+        // running two phases ahead on a shared stage would pass the parity test spuriously)
+        if (s % TC_PROD != warp) continue;
         const uint32_t ph = (uint32_t)(kb / S) & 1u;
         mbar_wait(empty(s), ph ^ 1u);
         mbar_expect_tx(full(s), TC_A_BYTES + Cfg::B_BYTES);
@@ -138,7 +201,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == TC_MMA_WARP) {
     // ===== MMA issuer (one lane) =====
     if (lane == 0) {
       const uint32_t idesc = make_idesc(KIND_TF32, g.a_mn, g.b_mn, TC_BM, BN);
@@ -162,7 +225,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int tb = kb & 1;                       // SPLIT: TMEM ping-pong buffer
         if (SPLIT) mbar_wait(tempty(tb), ((uint32_t)(kb >> 1) & 1u) ^ 1u);
         tcgen05_fence_after();
-        const uint32_t td = tmem_base + (SPLIT ? (uint32_t)(tb * BN) : 0u);
+        const uint32_t td = tmem_base + (SPLIT ? (uint32_t)(tb * NACC * BN) : 0u);
+        int idx = 0;   // MMA number inside the k-block -> accumulator idx % NACC
+        auto issue = [&](uint64_t a, uint64_t b) {
+          const uint32_t acc_on = SPLIT ? (idx >= NACC) : (kb > 0 || idx >= NACC);
+          umma<KIND_TF32>(td + (uint32_t)((idx % NACC) * BN), a, b, idesc, acc_on ? 1u : 0u);
+          ++idx;
+        };
 #pragma unroll
         for (int j = 0; j < TC_BK / 8; ++j) {
           const uint64_t ad = make_smem_desc(stA(s) + a_off(j), a_lbo, a_sbo, a_lay);
@@ -170,11 +239,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (SPLIT) {
             const uint64_t al = make_smem_desc(stAlo(s) + a_off(j), a_lbo, a_sbo, a_lay);
             const uint64_t bl = make_smem_desc(stBlo(s) + b_off(j), b_lbo, b_sbo, b_lay);
-            umma<KIND_TF32>(td, al, bd, idesc, j ? 1u : 0u);   // every k-block starts from zero
-            umma<KIND_TF32>(td, ad, bl, idesc, 1u);
-            umma<KIND_TF32>(td, ad, bd, idesc, 1u);
+            issue(al, bd);   // every k-block starts from zero (promotion, see header)
+            issue(ad, bl);
+            issue(ad, bd);
           } else {
-            umma<KIND_TF32>(td, ad, bd, idesc, (kb | j) ? 1u : 0u);
+            issue(ad, bd);
           }
         }
         umma_commit(empty(s));  // stage reusable once these MMAs have read it
@@ -183,8 +252,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (!SPLIT) umma_commit(accum);
     }
   } else {
-    // ===== transform + promotion (3xTF32) and epilogue: warps 2..5 =====
-    const int et = threadIdx.x - 64;  // 0..127
+    // ===== transform + promotion (3xTF32) and epilogue: warps 4..7 =====
+    const int et = threadIdx.x - 32 * TC_PROD;  // 0..127
     const int q = warp & 3;           // TMEM lane quarter this warp may read
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     float acc[SPLIT ? BN : 1];
@@ -198,11 +267,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tcgen05_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 16) {
-          uint32_t r[16];
-          tmem_ld16(tlane + (uint32_t)(tb * BN + c0), r);
-          tmem_ld_wait();
+          float part[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) acc[c0 + i] += __uint_as_float(r[i]);
+          for (int a = 0; a < NACC; ++a) {
+            uint32_t r[16];
+            tmem_ld16(tlane + (uint32_t)((tb * NACC + a) * BN + c0), r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              part[i] = a ? part[i] + __uint_as_float(r[i]) : __uint_as_float(r[i]);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[c0 + i] += part[i];
         }
         tcgen05_fence_before();
         mbar_arrive(tempty(tb));
@@ -258,65 +334,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 16; ++i) r[i] = acc[c0 + i];
       } else {
-        uint32_t u[16];
-        tmem_ld16(tlane + (uint32_t)c0, u);
-        tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) r[i] = __uint_as_float(u[i]);
+        for (int a = 0; a < NACC; ++a) {
+          uint32_t u[16];
+          tmem_ld16(tlane + (uint32_t)(a * BN + c0), u);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = a ? r[i] + __uint_as_float(u[i]) : __uint_as_float(u[i]);
+        }
       }
       if (!row_ok) continue;
 #pragma unroll
       for (int v4 = 0; v4 < 4; ++v4) {
         const int n = n0 + c0 + 4 * v4;
         if (n >= g.N) break;
-        float v[4] = {r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3]};
-        float mk[4] = {1.f, 1.f, 1.f, 1.f};
-        if (g.epi != 2) {
-          if (g.mask_on == 1) {
-            const Philox4 pr = philox_block(g.seed, TN_RNG_DROPOUT, step, sample0 + (uint32_t)m,
-                                            (uint32_t)(n >> 2));
-            mk[0] = pr.x < g.thr ? 1.f : 0.f;
-            mk[1] = pr.y < g.thr ? 1.f : 0.f;
-            mk[2] = pr.z < g.thr ? 1.f : 0.f;
-            mk[3] = pr.w < g.thr ? 1.f : 0.f;
-          } else if (g.mask_on == 2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (n + j < g.N) mk[j] = g.mask_inj[(size_t)m * g.N + n + j];
-          }
-        }
-        if (g.epi == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j < g.N) {
-              const float a = act_fwd(v[j] + g.bias[n + j], g.act, g.act_nn);
-              v[j] = g.mask_on ? a * mk[j] : a;
-              if (g.scale != 1.f) v[j] *= g.scale;
-            }
-          }
-        } else if (g.epi == 1 && g.aux) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (n + j < g.N) {
-              const float d = act_bwd_from_out(g.aux[(size_t)m * g.N + n + j], g.act, g.act_nn);
-              v[j] = (g.mask_on ? v[j] * mk[j] : v[j]) * d;
-            }
-          }
-        }
-        float *c = g.C + (size_t)m * g.ldc + n;
-        if (n + 3 < g.N) {
-          *reinterpret_cast<float4 *>(c) = make_float4(v[0], v[1], v[2], v[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (n + j < g.N) c[j] = v[j];
-        }
+        tc_epi_quad(g, m, n, r[4 * v4], r[4 * v4 + 1], r[4 * v4 + 2], r[4 * v4 + 3], step, sample0);
       }
     }
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == TC_MMA_WARP) {
     __syncwarp();
     tcgen05_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -429,7 +467,7 @@ int dense_tc_fwd(const float *x, const float *W, const float *bias, float *out, 
   TcArgs g{};
   g.C = out; g.ldc = n_out; g.M = B; g.N = n_out; g.K = n_in;
   g.epi = 0; g.bias = bias; g.mask_inj = mask_inj; g.ctl = ctl; g.seed = seed; g.thr = thr;
-  g.mask_on = mask_on; g.act = act; g.act_nn = act_nn; g.scale = scale;
+  g.mask_on = mask_on; g.ak = make_actk(act, (int)act_nn); g.scale = scale;
   // A = x (B x n_in, K contiguous); B[n][k] = W[k][n] (N contiguous)
   return gemm_tc(x, n_in, 0, W, n_out, 1, g, split, "tn_dense_fwd(tc)", st);
 }
@@ -441,7 +479,7 @@ int dense_tc_bwd_data(const float *gr, const float *W, float *dx, int B, int n_i
   TcArgs g{};
   g.C = dx; g.ldc = n_in; g.M = B; g.N = n_in; g.K = n_out;
   g.epi = 1; g.aux = prev_out; g.mask_inj = mask_inj; g.ctl = ctl; g.seed = seed; g.thr = thr;
-  g.mask_on = mask_on; g.act = act; g.act_nn = act_nn; g.scale = 1.f;
+  g.mask_on = mask_on; g.ak = make_actk(act, (int)act_nn); g.scale = 1.f;
   // A = g (B x n_out, K contiguous); B[n][k] = W[n][k] (K contiguous)
   return gemm_tc(gr, n_out, 0, W, n_out, 0, g, split, "tn_dense_bwd_data(tc)", st);
 }
@@ -450,7 +488,7 @@ int dense_tc_bwd_weights(const float *x, const float *gr, float *dW, int B, int 
                          int split, cudaStream_t st) {
   TcArgs g{};
   g.C = dW; g.ldc = n_out; g.M = n_in; g.N = n_out; g.K = B;
-  g.epi = 2; g.scale = 1.f;
+  g.epi = 2; g.scale = 1.f; g.ak = make_actk(TN_ACT_LINEAR, 0);
   // A[m][k] = x[k][m] (M contiguous); B[n][k] = g[k][n] (N contiguous)
   return gemm_tc(x, n_in, 1, gr, n_out, 1, g, split, "tn_dense_bwd_weights(tc)", st);
 }

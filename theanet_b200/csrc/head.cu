@@ -30,8 +30,9 @@ struct HeadArgs {
   uint32_t thr;
   int B, n_in, n_out;
   int below;              // 1: multiply dh by mask * act'(h) of the layer below
-  int mask_on, act;
-  float nn, inv_bg;
+  int mask_on;
+  ActK ak;
+  float inv_bg;
 };
 
 template <int NP, int NQ>
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadArgs a) {
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float d = act_bwd_from_out(hv[e], a.act, a.nn);
+          const float d = act_bwd_k(a.ak, hv[e]);
           v[e] = (a.mask_on ? v[e] * mk[e] : v[e]) * d;
         }
       }
@@ -301,7 +302,7 @@ extern "C" int tn_softmax_head_fwd_bwd(const float *h, const float *W, const flo
   a.B = B; a.n_in = n_in; a.n_out = n_out; a.below = below && dh;
   a.mask_on = !a.below ? 0 : (mask_inj_below ? 2 : (pkeep_below < 1.0 ? 1 : 0));
   TN_REQUIRE(a.mask_on != 1 || ctl, TN_ERR_ARG, "%s: dropout needs ctl", who);
-  a.act = act_below; a.nn = (float)nn_below; a.inv_bg = inv_global_batch;
+  a.ak = make_actk(act_below, nn_below); a.inv_bg = inv_global_batch;
   cudaStream_t st = (cudaStream_t)stream;
   if (n_out <= 8) return launch_head_q<8>(a, st);
   if (n_out <= 12) return launch_head_q<12>(a, st);

@@ -21,9 +21,18 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+#ifndef TN_EXPECT_MODE
+#define TN_EXPECT_MODE 0
+#endif
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+#if TN_EXPECT_MODE == 1
+  asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+               "r"(bytes)
+               : "memory");
+#else
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -73,6 +82,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
   if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
   __syncwarp();
+}
+
+// true in exactly one (hardware-chosen) lane of a fully converged warp.  Code that must be issued
+// by one thread (tcgen05.mma / commit, TMA) should sit in `if (elect_one()) {...}` inside
+// warp-uniform control flow: the compiler then keeps descriptors in uniform registers; a
+// threadIdx-based `if (lane == 0)` makes it wrap every UTCHMMA in an R2UR + ELECT loop
+// (~120 cycles per MMA measured, tools/micro/mma_bench.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t.reg .pred p;\n\t"
+      "elect.sync r|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- fences --------------------------------------------------------------------------------------
