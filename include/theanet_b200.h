@@ -142,6 +142,30 @@ int tn_convpool_bwd_data(const float *a, const float *pooled, const float *dtop,
                          int pad_lo, int out_sz, int act, int act_nn, int pool, int pool_out_sz,
                          int act_below, int nn_below, void *stream);
 
+/* ---- ConvLayer on tcgen05 tensor cores: bf16 implicit GEMM, NHWC activations (conv_tc.cu) -----
+ * For wide layers (C % 64 == 0, M % 64 == 0, mode 'same', output width a power of two <= 128):
+ * config C4 of BASELINE.json.  Activation tensors are NHWC bfloat16 (void*); filters are repacked
+ * from the float32 OIHW master copy with tn_conv2d_tc_pack_weights (dgrad = 0: [M][f*f][C],
+ * flipped, for fprop; dgrad = 1: [C][f*f][M] for dgrad).  Accumulation is float32. */
+int tn_conv2d_tc_supported(int C, int S, int M, int f, int out_sz);
+int tn_nchw_f32_to_nhwc_bf16(const float *x, void *y, int B, int C, int H, int W, void *stream);
+int tn_nhwc_bf16_to_nchw_f32(const void *x, float *y, int B, int C, int H, int W, void *stream);
+int tn_conv2d_tc_pack_weights(const float *W, void *Wp, int M, int C, int f, int dgrad,
+                              void *stream);
+/* a = act(conv(x) + b) (B,out,out,M) bf16; pooled (may be NULL) = 2x2 max-pool of a, fused
+ * (needs an even out_sz <= 16); act must be linear / relu / reluNN */
+int tn_conv2d_tc_fprop(const void *x, const void *Wp, const float *bias, void *a, void *pooled,
+                       int B, int C, int S, int M, int f, int pad_lo, int out_sz, int act,
+                       int act_nn, void *stream);
+/* dx (B,S,S,C) bf16 from gz (B,out,out,M) bf16 */
+int tn_conv2d_tc_dgrad(const void *gz, const void *Wp_dgrad, void *dx, int B, int C, int S, int M,
+                       int f, int pad_lo, int out_sz, void *stream);
+size_t tn_conv2d_tc_wgrad_workspace_bytes(int B, int C, int M, int f, int out_sz);
+/* dW (OIHW float32), db from x (B,S,S,C) and gz (B,out,out,M), both bf16; split-K partials in
+ * `workspace`, reduced in a fixed order (deterministic) */
+int tn_conv2d_tc_wgrad(const void *x, const void *gz, float *dW, float *db, void *workspace, int B,
+                       int C, int S, int M, int f, int pad_lo, int out_sz, void *stream);
+
 /* ---- PoolLayer (theanet/layer/convpool.py:97-127; pool_2d max, stride = window) ------------- */
 /* planes = B*C; out_sz = ceil(S/p) (ignore_border=False) or S/p */
 int tn_maxpool_fwd(const float *x, float *out, int planes, int S, int p, int out_sz,

@@ -55,6 +55,14 @@ SIGNATURES = {
     'tn_convpool_bwd_weights_workspace_bytes': (C.c_size_t, [_I] * 4),
     'tn_convpool_bwd_weights': (_I, [_P] * 7 + [_I] * 11 + [_P]),
     'tn_convpool_bwd_data': (_I, [_P] * 6 + [_I] * 13 + [_P]),
+    'tn_conv2d_tc_supported': (_I, [_I] * 5),
+    'tn_nchw_f32_to_nhwc_bf16': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'tn_nhwc_bf16_to_nchw_f32': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'tn_conv2d_tc_pack_weights': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'tn_conv2d_tc_fprop': (_I, [_P] * 5 + [_I] * 9 + [_P]),
+    'tn_conv2d_tc_dgrad': (_I, [_P] * 3 + [_I] * 7 + [_P]),
+    'tn_conv2d_tc_wgrad_workspace_bytes': (C.c_size_t, [_I] * 5),
+    'tn_conv2d_tc_wgrad': (_I, [_P] * 5 + [_I] * 7 + [_P]),
     'tn_maxpool_fwd': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_maxpool_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     'tn_dense_fwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _D, _U64, _P, _P, _F, _P]),
