@@ -71,6 +71,9 @@ template <int BN>
 __global__ void __launch_bounds__(CT_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const ConvTcArgs g) {
+  // Persistent: every CTA walks the (pixel tile, channel tile) work list with stride gridDim.x.
+  // The shared-memory ring and its phases run on across tiles; the accumulator is double-buffered
+  // in TMEM (2 x 256 columns) so that the epilogue of tile i overlaps the main loop of tile i+1.
   using Cfg = ConvTcCfg<BN>;
   constexpr int S = Cfg::STAGES;
   constexpr int NACC = Cfg::NACC;
@@ -79,16 +82,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const uint32_t bar0 = base + S * Cfg::STAGE_BYTES;
   auto full = [&](int s) { return bar0 + 8u * s; };
   auto empty = [&](int s) { return bar0 + 8u * (S + s); };
-  const uint32_t accum = bar0 + 8u * (2 * S);
-  const uint32_t tslot = accum + 8u;
+  auto tfull = [&](int b) { return bar0 + 8u * (2 * S + b); };
+  auto tempty = [&](int b) { return bar0 + 8u * (2 * S + 2 + b); };
+  const uint32_t tslot = bar0 + 8u * (2 * S + 4);
   auto stA = [&](int s) { return base + s * Cfg::STAGE_BYTES; };
   auto stB = [&](int s) { return base + s * Cfg::STAGE_BYTES + CT_A_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * BN;
-  // tile -> (first image, first output row)
   const int tiles_y = g.Ho / g.TH;
-  const int b0 = (blockIdx.x / tiles_y) * g.TB, y0 = (blockIdx.x % tiles_y) * g.TH;
+  const int mtiles = ((g.B + g.TB - 1) / g.TB) * tiles_y;
+  const int ntiles = (g.N + BN - 1) / BN;
+  const int nwork = mtiles * ntiles;
   const int cchunks = g.C >> 6;
   const int nkb = g.f * g.f * cchunks;
 
@@ -99,10 +103,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(full(s), 1);
       mbar_init(empty(s), 1);
     }
-    mbar_init(accum, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull(b), 1);
+      mbar_init(tempty(b), 128);
+    }
     fence_barrier_init();
   }
-  if (warp == CT_MMA_WARP) tmem_alloc(tslot, Cfg::TMEM_COLS);
+  if (warp == CT_MMA_WARP) tmem_alloc(tslot, 2 * Cfg::TMEM_COLS);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -111,97 +118,127 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   if (warp < CT_PROD) {
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        if (s % CT_PROD != warp) continue;   // one owner per stage: phases stay in order
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
-        mbar_wait(empty(s), ph ^ 1u);
-        mbar_expect_tx(full(s), CT_A_BYTES + Cfg::B_BYTES);
-        const int tap = kb / cchunks, cc = kb - tap * cchunks;
-        const int r = tap / g.f, sx = tap - r * g.f;
-        tma_load_4d(stA(s), &tmX, full(s), cc * 64, sx - g.pad, y0 + r - g.pad, b0);
-        tma_load_2d(stB(s), &tmW, full(s), tap * g.C + cc * 64, n0);
+      int it = 0;   // running k-block counter across tiles
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int mt = w / ntiles, n0 = (w - mt * ntiles) * BN;   // channel tiles of a pixel tile are neighbours
+        const int b0 = (mt / tiles_y) * g.TB, y0 = (mt % tiles_y) * g.TH;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          if (s % CT_PROD != warp) continue;   // one owner per stage: phases stay in order
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty(s), ph ^ 1u);
+          mbar_expect_tx(full(s), CT_A_BYTES + Cfg::B_BYTES);
+          const int tap = kb / cchunks, cc = kb - tap * cchunks;
+          const int r = tap / g.f, sx = tap - r * g.f;
+          tma_load_4d(stA(s), &tmX, full(s), cc * 64, sx - g.pad, y0 + r - g.pad, b0);
+          tma_load_2d(stB(s), &tmW, full(s), tap * g.C + cc * 64, n0);
+        }
       }
     }
   } else if (warp == CT_MMA_WARP) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(KIND_BF16, 0, 0, 128, BN);
-      int idx = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
-        mbar_wait(full(s), ph);
+      int it = 0, ti = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++ti) {
+        const int ab = ti & 1;
+        mbar_wait(tempty(ab), ((uint32_t)(ti >> 1) & 1u) ^ 1u);   // epilogue drained this buffer
         tcgen05_fence_after();
+        const uint32_t td = tmem_base + (uint32_t)(ab * Cfg::TMEM_COLS);
+        int idx = 0;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(full(s), ph);
+          tcgen05_fence_after();
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {   // 64 channels = 4 x K16
-          const uint64_t ad = make_smem_desc(stA(s) + j * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(stB(s) + j * 32, 16, 1024);
-          umma<KIND_BF16>(tmem_base + (uint32_t)((idx % NACC) * BN), ad, bd, idesc,
-                          idx >= NACC ? 1u : 0u);
-          ++idx;
+          for (int j = 0; j < 4; ++j) {   // 64 channels = 4 x K16
+            const uint64_t ad = make_smem_desc(stA(s) + j * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(stB(s) + j * 32, 16, 1024);
+            umma<KIND_BF16>(td + (uint32_t)((idx % NACC) * BN), ad, bd, idesc, idx >= NACC ? 1u : 0u);
+            ++idx;
+          }
+          umma_commit(empty(s));
         }
-        umma_commit(empty(s));
+        umma_commit(tfull(ab));
       }
-      umma_commit(accum);
     }
   } else {
     // ===== epilogue: one output pixel per thread =====
-    mbar_wait(accum, 0);
-    tcgen05_fence_after();
     const int q = warp & 3;
     const int row = q * 32 + lane;               // pixel inside the tile
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int per_img = g.TH * g.Wo;
     const int bl = row / per_img, rem = row - bl * per_img;
     const int yl = rem / g.Wo, xo = rem - yl * g.Wo;
-    const int b = b0 + bl, y = y0 + yl;
-    const bool ok = b < g.B;
-    __nv_bfloat16 *orow = g.out + (((size_t)b * g.Ho + y) * g.Wo + xo) * g.N + n0;
     const bool pool = g.pooled != nullptr;
-    const bool writer = pool && ((xo | y) & 1) == 0;
-    __nv_bfloat16 *prow = pool ? g.pooled + (((size_t)b * (g.Ho >> 1) + (y >> 1)) * (g.Wo >> 1) + (xo >> 1)) * g.N + n0
-                               : nullptr;
+    const float sl = g.ak.act == TN_ACT_LINEAR ? 1.f : g.ak.s_neg;
+    int ti = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++ti) {
+      const int mt = w / ntiles, n0 = (w - mt * ntiles) * BN;
+      const int b = (mt / tiles_y) * g.TB + bl, y = (mt % tiles_y) * g.TH + yl;
+      const bool ok = b < g.B;
+      const int ab = ti & 1;
+      mbar_wait(tfull(ab), (uint32_t)(ti >> 1) & 1u);
+      tcgen05_fence_after();
+      const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * Cfg::TMEM_COLS);
+      __nv_bfloat16 *orow = g.out + (((size_t)b * g.Ho + y) * g.Wo + xo) * g.N + n0;
+      const bool writer = pool && ((xo | y) & 1) == 0;
+      __nv_bfloat16 *prow =
+          pool ? g.pooled + (((size_t)b * (g.Ho >> 1) + (y >> 1)) * (g.Wo >> 1) + (xo >> 1)) * g.N + n0
+               : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= g.N) break;
-      float v[16];
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        if (n0 + c0 >= g.N) break;
+        float v[16];
 #pragma unroll
-      for (int a = 0; a < NACC; ++a) {
-        uint32_t u[16];
-        tmem_ld16(tlane + (uint32_t)(a * BN + c0), u);
-        tmem_ld_wait();
+        for (int a = 0; a < NACC; ++a) {
+          uint32_t u[16];
+          tmem_ld16(tlane + (uint32_t)(a * BN + c0), u);
+          tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = a ? v[i] + __uint_as_float(u[i]) : __uint_as_float(u[i]);
-      }
-      if (g.bias) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = act_fwd_t<false>(g.ak, v[i] + g.bias[n0 + c0 + i]);
-      }
-      uint32_t pk[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-      if (ok) {
-        uint4 *o = reinterpret_cast<uint4 *>(orow + c0);
-        o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-      }
-      if (pool) {   // 2x2 max over the bf16-rounded values: partners are lanes ^1 and ^Wo
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 m = *reinterpret_cast<__nv_bfloat162 *>(&pk[i]);
-          uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
-          m = __hmax2(m, *reinterpret_cast<__nv_bfloat162 *>(&o1));
-          uint32_t mm = *reinterpret_cast<uint32_t *>(&m);
-          uint32_t o2 = __shfl_xor_sync(0xffffffffu, mm, g.Wo);
-          m = __hmax2(m, *reinterpret_cast<__nv_bfloat162 *>(&o2));
-          pk[i] = *reinterpret_cast<uint32_t *>(&m);
+          for (int i = 0; i < 16; ++i) v[i] = a ? v[i] + __uint_as_float(u[i]) : __uint_as_float(u[i]);
         }
-        if (writer && ok) {
-          uint4 *o = reinterpret_cast<uint4 *>(prow + c0);
+        if (g.bias) {   // bias + ReLU-family activation; the negative slope is a plain multiply
+                        // (the exact (z*NN)/100 of the fp32 path is below bf16 resolution)
+          const float4 *b4 = reinterpret_cast<const float4 *>(g.bias + n0 + c0);
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 bb = __ldg(b4 + i4);
+            const float bv[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float z = v[4 * i4 + e] + bv[e];
+              v[4 * i4 + e] = z > 0.f ? z : z * sl;
+            }
+          }
+        }
+        uint32_t pk[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (ok) {
+          uint4 *o = reinterpret_cast<uint4 *>(orow + c0);
           o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
         }
+        if (pool) {   // 2x2 max over the bf16-rounded values: partners are lanes ^1 and ^Wo
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 m = *reinterpret_cast<__nv_bfloat162 *>(&pk[i]);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[i], 1);
+            m = __hmax2(m, *reinterpret_cast<__nv_bfloat162 *>(&o1));
+            uint32_t mm = *reinterpret_cast<uint32_t *>(&m);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, mm, g.Wo);
+            m = __hmax2(m, *reinterpret_cast<__nv_bfloat162 *>(&o2));
+            pk[i] = *reinterpret_cast<uint32_t *>(&m);
+          }
+          if (writer && ok) {
+            uint4 *o = reinterpret_cast<uint4 *>(prow + c0);
+            o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
       }
+      tcgen05_fence_before();
+      mbar_arrive(tempty(ab));   // 128 arrivals hand the accumulator buffer back to the MMA lane
     }
   }
   tcgen05_fence_before();
@@ -209,7 +246,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == CT_MMA_WARP) {
     __syncwarp();
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, 2 * Cfg::TMEM_COLS);
   }
 }
 
@@ -364,23 +401,36 @@ __global__ void conv_tc_wgrad_finish_kernel(const float *__restrict__ partial, i
   }
 }
 
-// db[m] = sum_p gz[p][m] (bf16 NHWC, fp32 accumulate): 64 channels x 16 pixel-slices per CTA
+// db[m] = sum_p gz[p][m] (bf16 NHWC, fp32 accumulate), two fixed-order stages:
+// stage 1: CTA (channel block of 64, pixel slice) -> partial[slice][m]; stage 2 adds the slices.
+constexpr int kColSlices = 128;
 __global__ void __launch_bounds__(1024)
-colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ gz, int64_t P, int M, float *__restrict__ db) {
+colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ gz, int64_t P, int M,
+                   float *__restrict__ partial) {
   __shared__ float red[16][65];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   const int m = blockIdx.x * 64 + tx;
+  const int64_t per = (P + gridDim.y - 1) / gridDim.y;
+  const int64_t p0 = blockIdx.y * per, p1 = p0 + per < P ? p0 + per : P;
   float s = 0.f;
   if (m < M)
-    for (int64_t p = ty; p < P; p += 16) s += __bfloat162float(gz[p * M + m]);
+    for (int64_t p = p0 + ty; p < p1; p += 16) s += __bfloat162float(gz[p * M + m]);
   red[ty][tx] = s;
   __syncthreads();
   if (ty == 0 && m < M) {
     float t = red[0][tx];
 #pragma unroll
     for (int k = 1; k < 16; ++k) t += red[k][tx];
-    db[m] = t;
+    partial[(size_t)blockIdx.y * M + m] = t;
   }
+}
+__global__ void colsum_finish_kernel(const float *__restrict__ partial, int nslices, int M,
+                                     float *__restrict__ db) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  float s = 0.f;
+  for (int k = 0; k < nslices; ++k) s += partial[(size_t)k * M + m];
+  db[m] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -506,8 +556,8 @@ static int launch_conv_tc(const CUtensorMap &tmX, const CUtensorMap &tmW, const 
   auto k = conv_tc_kernel<BN>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   TN_REQUIRE(e == cudaSuccess, TN_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
-  dim3 grid(ceil_div(g.B, g.TB) * (g.Ho / g.TH), ceil_div(g.N, BN));
-  k<<<grid, CT_THREADS, Cfg::SMEM, st>>>(tmX, tmW, g);
+  const int nwork = ceil_div(g.B, g.TB) * (g.Ho / g.TH) * ceil_div(g.N, BN);
+  k<<<nwork < kNumSM ? nwork : kNumSM, CT_THREADS, Cfg::SMEM, st>>>(tmX, tmW, g);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
 }
@@ -617,7 +667,7 @@ extern "C" size_t tn_conv2d_tc_wgrad_workspace_bytes(int B, int C, int M, int f,
   if (tile_geom(out_sz, out_sz, &th, &tb, "tn_conv2d_tc_wgrad_workspace_bytes")) return 0;
   const int ptiles = ceil_div(B, tb) * (out_sz / th);
   const int tiles_out = f * f * (C / WG_BN) * ceil_div(M, 128);
-  return (size_t)wgrad_split(tiles_out, ptiles) * f * f * M * C * sizeof(float);
+  return ((size_t)wgrad_split(tiles_out, ptiles) * f * f * M * C + (size_t)kColSlices * M) * sizeof(float);
 }
 
 extern "C" int tn_conv2d_tc_wgrad(const void *x, const void *gz, float *dW, float *db,
@@ -648,8 +698,11 @@ extern "C" int tn_conv2d_tc_wgrad(const void *x, const void *gz, float *dW, floa
   conv_tc_wgrad_finish_kernel<<<blocks_for((int64_t)f * f * M * C), 256, 0, st>>>(
       (const float *)workspace, g.nsplit, M, C, f, dW);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(finish)");
-  colsum_bf16_kernel<<<ceil_div(M, 64), 1024, 0, st>>>((const __nv_bfloat16 *)gz,
-                                                        (int64_t)B * out_sz * out_sz, M, db);
+  float *cpart = (float *)workspace + (size_t)g.nsplit * f * f * M * C;
+  colsum_bf16_kernel<<<dim3(ceil_div(M, 64), kColSlices), 1024, 0, st>>>(
+      (const __nv_bfloat16 *)gz, (int64_t)B * out_sz * out_sz, M, cpart);
+  TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(db partial)");
+  colsum_finish_kernel<<<ceil_div(M, 128), 128, 0, st>>>(cpart, kColSlices, M, db);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(db)");
   return TN_OK;
 }
