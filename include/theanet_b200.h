@@ -160,6 +160,11 @@ int tn_conv2d_tc_fprop(const void *x, const void *Wp, const float *bias, void *a
 /* dx (B,S,S,C) bf16 from gz (B,out,out,M) bf16 */
 int tn_conv2d_tc_dgrad(const void *gz, const void *Wp_dgrad, void *dx, int B, int C, int S, int M,
                        int f, int pad_lo, int out_sz, void *stream);
+/* gz = [a == pooled(2x2 window)] * dtop * act'(a), NHWC bf16 (every tied maximum receives the
+ * gradient).  dtop: float32 NCHW (B,M,S/2,S/2) if dtop_nchw_f32 else bf16 NHWC; pooled == NULL:
+ * no pool layer, dtop has the shape of a. */
+int tn_poolbwd_nhwc_bf16(const void *a, const void *pooled, const void *dtop, int dtop_nchw_f32,
+                         void *gz, int B, int S, int M, int act, int act_nn, void *stream);
 size_t tn_conv2d_tc_wgrad_workspace_bytes(int B, int C, int M, int f, int out_sz);
 /* dW (OIHW float32), db from x (B,S,S,C) and gz (B,out,out,M), both bf16; split-K partials in
  * `workspace`, reduced in a fixed order (deterministic) */

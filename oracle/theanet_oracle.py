@@ -356,6 +356,27 @@ class InjectedRandom:
 # ----------------------------------------------------------------------------------------------
 # The network -- theanet/neuralnet.py:59-333
 # ----------------------------------------------------------------------------------------------
+def bf16_round(a):
+    """float32 -> bfloat16 (round to nearest even) -> float32, the rounding the tensor-core conv
+    path applies to its operands and outputs (theanet_b200/csrc/conv_tc.cu)."""
+    u = np.ascontiguousarray(a, np.float32).view(np.uint32)
+    r = (u + np.uint32(0x7fff) + ((u >> np.uint32(16)) & np.uint32(1))) & np.uint32(0xffff0000)
+    return r.view(np.float32).reshape(np.shape(a))
+
+
+def conv_tc_eligible(in_maps, in_sz, M, f, mode, actvn, out_sz, pool_sz=None, ignore_border=False):
+    """Which ConvLayers theanet_b200 runs as bf16 tensor-core implicit GEMMs when
+    training_params['CONV_DTYPE'] == 'bfloat16' (mirrors NeuralNet._conv_tc_ok)."""
+    fast = actvn in ('linear', 'relu') or (len(actvn) == 6 and actvn.startswith('relu'))
+    if not (in_maps % 64 == 0 and M % 64 == 0 and mode == 'same' and fast and 1 <= f <= 7):
+        return False
+    if out_sz < 4 or out_sz > 128 or out_sz & (out_sz - 1):
+        return False
+    if pool_sz is not None and (pool_sz != 2 or out_sz > 16 or ignore_border):
+        return False
+    return True
+
+
 class OracleNet:
     """Eager numpy twin of NeuralNet: same constructor arguments, same RNG consumption order for
     initialisation, same train/test semantics.
@@ -442,6 +463,20 @@ class OracleNet:
             if L['params']:
                 L['vel'] = [np.zeros_like(p) for p in L['params']]
             self.spec.append(L)
+        # NOT reference behaviour: theanet_b200's optional mixed-precision conv stack (config C4).
+        # The restatement rounds the same tensors to bfloat16 at the same points so that the
+        # tensor-core path can be checked tightly (float32 accumulation on both sides).
+        bf16 = str(training_params.get('CONV_DTYPE', 'float32')).lower() in ('bf16', 'bfloat16')
+        for li, L in enumerate(self.spec):
+            L['tc'] = False
+            if bf16 and L['kind'] == 'ConvLayer':
+                nxt = self.spec[li + 1] if li + 1 < len(self.spec) else None
+                pool = nxt['args'] if nxt is not None and nxt['kind'] == 'PoolLayer' else None
+                in_sz = self.spec[li - 1].get('out_sz')
+                L['tc'] = conv_tc_eligible(
+                    L['in_maps'], in_sz, L['num_maps'], L['args']['filter_sz'], L['mode'], L['actvn'],
+                    L['out_sz'], pool['pool_sz'] if pool else None,
+                    pool.get('ignore_border', False) if pool else False)
         if 'CUR_EPOCH' not in training_params:                               # neuralnet.py:108-109
             training_params['CUR_EPOCH'] = 0
         self.set_rate()
@@ -496,10 +531,15 @@ class OracleNet:
                 if a.ndim != 4:
                     raise ValueError("conv after a dense layer")
                 W, b = L['params']
+                if L['tc']:                                  # bf16 operands, float32 accumulate
+                    a, W = bf16_round(a).astype(dt), bf16_round(W).astype(dt)
+                    c['Wr'] = W
                 z, cc = conv_forward(a, W, L['mode'])
                 z = z + b[None, :, None, None]
                 c.update(cc=cc, z=z)
                 a = act_forward(L['actvn'], z)
+                if L['tc']:
+                    a = bf16_round(a).astype(dt)             # activations are stored in bf16
                 c['a'] = a
             elif kind == 'PoolLayer':
                 a, pc = pool_forward(a, args['pool_sz'], args.get('ignore_border', False))
@@ -592,7 +632,11 @@ class OracleNet:
             elif kind == 'ConvLayer':
                 W, b = L['params']
                 gz = act_backward(L['actvn'], c['z'], c['a'], g)
+                if L['tc']:
+                    gz, W = bf16_round(gz).astype(dt), c['Wr']
                 dW, db, dx = conv_backward(gz, W, c['cc'], need_dx=li > first_weighted)
+                if L['tc'] and dx is not None:
+                    dx = bf16_round(dx).astype(dt)
                 grads[li] = [dW, db]
                 g = dx
             else:

@@ -315,6 +315,26 @@ def test_conv_wgrad_many_images_is_deterministic(C):
     assert rel(res[0][0], dW) < 1e-4 and rel(res[0][1], db) < 1e-4
 
 
+def test_conv_wgrad_row_bands_large_image(C):
+    """C4 conv 1: 3 -> 64 maps on 32x32 ('same'): dL/dz of one image (256 KB) does not fit in shared
+    memory, the direct wgrad kernel walks it in bands of output rows."""
+    B, Cin, S, M, f = 5, 3, 32, 64, 3
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((B, Cin, S, S)).astype(np.float32)
+    gz = rng.standard_normal((B, M, S, S)).astype(np.float32)
+    W = np.zeros((M, Cin, f, f), np.float32)
+    pad_lo, out_sz = O.conv_geometry(S, f, 'same')
+    _, cache = O.conv_forward(x.astype(np.float64), W.astype(np.float64), 'same')
+    dW, db, _ = O.conv_backward(gz.astype(np.float64), W.astype(np.float64), cache, need_dx=False)
+    nb = C.lib.tn_conv2d_wgrad_workspace_bytes(B, Cin, S, M, f)
+    ws = torch.zeros(nb // 4 + 1, device='cuda')
+    dWd, dbd = torch.zeros((M, Cin, f, f), device='cuda'), torch.zeros(M, device='cuda')
+    C.call('tn_conv2d_wgrad', C.ptr(dev(x)), C.ptr(dev(gz)), C.ptr(dWd), C.ptr(dbd), C.ptr(ws), B, Cin,
+           S, M, f, pad_lo, out_sz, None)
+    sync()
+    assert rel(dWd.cpu().numpy(), dW) < 1e-5 and rel(dbd.cpu().numpy(), db) < 1e-5
+
+
 def test_conv_direct_path_refuses_oversized_shapes(C):
     x = torch.zeros((1, 64, 32, 32), device='cuda')
     W = torch.zeros((128, 64, 3, 3), device='cuda')

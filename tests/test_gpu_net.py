@@ -232,3 +232,55 @@ def test_elastic_debugout_matches_oracle_field():
     fm = philox.bernoulli_mask(seed, philox.PURPOSE_FLIP, 1, np.arange(8), 784, .03).reshape(8, 1, 28, 28)
     want = O.elastic_apply(x[8:16], prms['layers'][0][1], ty, tx, fm)
     assert np.mean(net.out[0].cpu().numpy() == want) > 0.999
+
+
+# --------------------------------------------------------------------------------------------
+# config C4: CIFAR-shaped 3-conv network, bf16 tensor-core conv stack
+# --------------------------------------------------------------------------------------------
+TOL_BF16 = 1e-2     # bf16 conv stack vs the restatement that rounds the same tensors to bf16: what
+                    # is left is accumulation order plus values that straddle a bf16 rounding
+                    # boundary (one bf16 ulp = 4e-3 relative on single elements)
+
+
+def rel2(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_cifar3conv_bf16_tensor_core_stack_matches_oracle():
+    from theanet_b200.neuralnet import NeuralNet
+    B = 8
+    prms = load_prms('cifar3conv.prms', B, 32, seed=31337)
+    prms['training_params']['CONV_DTYPE'] = 'bfloat16'
+    x, y = synth(2 * B, 3, 32, 10, dense=True)
+    p1, p2 = copy.deepcopy(prms), copy.deepcopy(prms)
+    net = NeuralNet(p1['layers'], p1['training_params'])
+    assert sorted(net.conv_tc) == [3, 5]              # conv 2 and conv 3 on tcgen05, conv 1 direct
+    on = O.OracleNet(p2['layers'], p2['training_params'])
+    assert [L['tc'] for L in on.spec if L['kind'] == 'ConvLayer'] == [False, True, True]
+    fn = net.get_trin_model(x, y)
+    for s in range(3):
+        i = s % 2
+        cost, _, lp = fn(i)
+        ocost, olp = on.train_step(x[i * B:(i + 1) * B], y[i * B:(i + 1) * B], step=s, sample0=0)
+        tol = TOL_BF16 if s < 2 else 3 * TOL_BF16
+        assert abs(cost - ocost) <= tol * abs(ocost), (s, cost, ocost)
+        assert rel(lp, olp) < tol, (s, rel(lp, olp))
+        if s >= 2:
+            # lagged momentum: steps 0 and 1 run on identical weights; from step 2 on the two
+            # sides train on weights that differ in the last bits, and bf16 rounding of the
+            # activations amplifies that (a different path through the same noise, not an error)
+            continue
+        # gradients in the relative L2 norm: an activation that straddles a bf16 rounding boundary
+        # flips a max-pool tie and moves single gradient entries by whole contributions (at B = 8
+        # that is percents of the largest entry), without touching the bulk of the tensor
+        for li, (gg, og) in enumerate(zip(net.get_gradients(), on.last_grads)):
+            for k, u in enumerate(gg):
+                assert rel2(u, og[k]) < TOL_BF16, 'step {} grad layer {} tensor {}: {}'.format(
+                    s, li, k, rel2(u, og[k]))
+    for a, b in zip(net.get_init_params()['allwts'], on.get_wts()):
+        for u, v in zip(a, b):
+            assert rel2(u, v) < TOL_BF16
+    e, pr = net.get_test_model(x, y)(0)
+    oe, opr, _, _ = on.test_step(x[:B], y[:B])
+    assert abs(e - oe) < 1e-6 and abs(pr - opr) <= TOL_BF16 * opr

@@ -136,6 +136,7 @@ struct WgradArgs {
   const float *gz;  // (B, M, out, out) dL/dz
   float *partial;   // [grid][OG*4 + mP]
   int B, C, S, M, f, pad_lo, out_sz;
+  int RB;           // output rows staged per pass (a band of the image)
 };
 
 template <int F>
@@ -147,8 +148,9 @@ __global__ void __launch_bounds__(1024) conv_wgrad_kernel(WgradArgs a) {
   const int npix = a.out_sz * a.out_sz;
   const int OG = G * a.C * f * f;
   const int PS = max(1, (int)blockDim.x / OG);
-  float *gs = smem;                      // [npix][mP]
-  float *xs = smem + (size_t)npix * mP;  // [C][Sp][Sp]
+  const int RB = a.RB;
+  float *gs = smem;                               // [RB*out_sz][mP]
+  float *xs = smem + (size_t)RB * a.out_sz * mP;  // [C][RB+f-1][Sp]
   const int tid = threadIdx.x;
   const bool active = tid < OG * PS;
   const int slice = tid / OG, og = tid % OG;
@@ -163,36 +165,40 @@ __global__ void __launch_bounds__(1024) conv_wgrad_kernel(WgradArgs a) {
 
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     const float *gimg = a.gz + (size_t)b * a.M * npix;
-    for (int t = tid; t < npix * mP; t += blockDim.x) {
-      const int m = t / npix, p = t - m * npix;  // coalesced global read, transposed shared store
-      gs[p * mP + m] = m < a.M ? gimg[t] : 0.f;
-    }
     const float *img = a.x + (size_t)b * a.C * a.S * a.S;
-    for (int t = tid; t < a.C * Sp * Sp; t += blockDim.x) {
-      const int X = t % Sp;
-      int r = t / Sp;
-      const int Y = r % Sp;
-      const int ci = r / Sp;
-      const int y = Y - a.pad_lo, x = X - a.pad_lo;
-      xs[t] = (y >= 0 && y < a.S && x >= 0 && x < a.S) ? img[(ci * a.S + y) * a.S + x] : 0.f;
-    }
-    __syncthreads();
-    if (active) {
-      const float *xp = xs + (c * Sp + u) * Sp + v;
-      for (int p = slice; p < npix; p += PS) {
-        const int i = p / a.out_sz, j = p - i * a.out_sz;
-        const float xv = xp[i * Sp + j];
-        const float4 g = gs4[p * G + mg];
-        acc.x = fmaf(xv, g.x, acc.x);
-        acc.y = fmaf(xv, g.y, acc.y);
-        acc.z = fmaf(xv, g.z, acc.z);
-        acc.w = fmaf(xv, g.w, acc.w);
-        if (is_db) {
-          dba.x += g.x; dba.y += g.y; dba.z += g.z; dba.w += g.w;
+    for (int r0 = 0; r0 < a.out_sz; r0 += RB) {   // bands of output rows: large images fit in smem
+      const int nr = min(RB, a.out_sz - r0);
+      const int bpix = nr * a.out_sz, xr = nr + f - 1;
+      for (int t = tid; t < bpix * mP; t += blockDim.x) {
+        const int m = t / bpix, p = t - m * bpix;  // coalesced global read, transposed shared store
+        gs[p * mP + m] = m < a.M ? gimg[m * npix + r0 * a.out_sz + p] : 0.f;
+      }
+      for (int t = tid; t < a.C * xr * Sp; t += blockDim.x) {
+        const int X = t % Sp;
+        int r = t / Sp;
+        const int Y = r % xr;
+        const int ci = r / xr;
+        const int y = r0 + Y - a.pad_lo, x = X - a.pad_lo;
+        xs[t] = (y >= 0 && y < a.S && x >= 0 && x < a.S) ? img[(ci * a.S + y) * a.S + x] : 0.f;
+      }
+      __syncthreads();
+      if (active) {
+        const float *xp = xs + (c * xr + u) * Sp + v;
+        for (int p = slice; p < bpix; p += PS) {
+          const int i = p / a.out_sz, j = p - i * a.out_sz;
+          const float xv = xp[i * Sp + j];
+          const float4 g = gs4[p * G + mg];
+          acc.x = fmaf(xv, g.x, acc.x);
+          acc.y = fmaf(xv, g.y, acc.y);
+          acc.z = fmaf(xv, g.z, acc.z);
+          acc.w = fmaf(xv, g.w, acc.w);
+          if (is_db) {
+            dba.x += g.x; dba.y += g.y; dba.z += g.z; dba.w += g.w;
+          }
         }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
   // reduce the PS pixel slices in a fixed order (shared memory reused)
   float4 *red = reinterpret_cast<float4 *>(smem);  // [PS][OG] then [PS][G]
@@ -304,8 +310,13 @@ extern "C" int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float
   const int PS = max(1, kConvThreads / OG);
   const int threads = ((OG * PS + 31) / 32) * 32;
   const int Sp = out_sz + f - 1;
-  const int npix = out_sz * out_sz;
-  size_t smem = ((size_t)npix * mP + (size_t)C * Sp * Sp) * sizeof(float);
+  // rows per band: the whole image when it fits in ~96 KB, else as many rows as do
+  int RB = out_sz;
+  auto band_bytes = [&](int rb) {
+    return ((size_t)rb * out_sz * mP + (size_t)C * (rb + f - 1) * Sp) * sizeof(float);
+  };
+  while (RB > 1 && band_bytes(RB) > 96 * 1024) RB = (RB + 1) / 2;
+  size_t smem = band_bytes(RB);
   const size_t red = (size_t)PS * OG * 16;
   if (red > smem) smem = red;
   TN_REQUIRE(smem <= 220 * 1024, TN_ERR_UNSUPPORTED,
@@ -316,7 +327,7 @@ extern "C" int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float
     TN_REQUIRE(e == cudaSuccess, TN_ERR_CUDA, "tn_conv2d_wgrad: %s", cudaGetErrorString(e));
   }
   const int grid = wgrad_grid(B);
-  WgradArgs a{x, gz, (float *)workspace, B, C, S, M, f, pad_lo, out_sz};
+  WgradArgs a{x, gz, (float *)workspace, B, C, S, M, f, pad_lo, out_sz, RB};
   cudaStream_t st = (cudaStream_t)stream;
   k<<<grid, threads, smem, st>>>(a);
   TN_LAUNCH_CHECK("tn_conv2d_wgrad");

@@ -483,6 +483,38 @@ __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, fl
   }
 }
 
+// gz[b,y,x,m] = [a == pooled(window)] * dtop(window) * act'(a)   (2x2 windows, NHWC bf16 a / pooled;
+// every tied maximum receives the gradient, as Theano's MaxPoolGrad).  dtop is either float32 NCHW
+// (B, M, P, P) -- the gradient arriving from a dense layer -- or bf16 NHWC (B, P, P, M) -- the dx of
+// the tensor-core conv above.  Without a pool layer (pooled == null) dtop has the shape of a.
+__global__ void poolbwd_nhwc_kernel(const __nv_bfloat16 *__restrict__ a,
+                                    const __nv_bfloat16 *__restrict__ pooled,
+                                    const void *__restrict__ dtop, int dtop_nchw_f32,
+                                    __nv_bfloat16 *__restrict__ gz, int64_t total, int S, int M,
+                                    ActK ak) {
+  const int P = S >> 1;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (int64_t)gridDim.x * blockDim.x) {
+    const int m = (int)(t % M);
+    int64_t rr = t / M;
+    const int x = (int)(rr % S); rr /= S;
+    const int y = (int)(rr % S);
+    const int64_t b = rr / S;
+    const float av = __bfloat162float(a[t]);
+    float g = 0.f;
+    if (pooled) {
+      const int64_t o = ((b * P + (y >> 1)) * P + (x >> 1)) * M + m;
+      if (a[t] == pooled[o])
+        g = dtop_nchw_f32 ? reinterpret_cast<const float *>(dtop)[((b * M + m) * P + (y >> 1)) * P + (x >> 1)]
+                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(dtop)[o]);
+    } else {
+      g = dtop_nchw_f32 ? reinterpret_cast<const float *>(dtop)[((b * M + m) * S + y) * S + x]
+                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(dtop)[t]);
+    }
+    gz[t] = __float2bfloat16_rn(g * act_bwd_t<false>(ak, av));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -609,6 +641,20 @@ extern "C" int tn_nhwc_bf16_to_nchw_f32(const void *x, float *y, int B, int C, i
   nhwc_bf16_to_nchw_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)x, y, total, C, H * W);
   TN_LAUNCH_CHECK("tn_nhwc_bf16_to_nchw_f32");
+  return TN_OK;
+}
+
+extern "C" int tn_poolbwd_nhwc_bf16(const void *a, const void *pooled, const void *dtop,
+                                    int dtop_nchw_f32, void *gz, int B, int S, int M, int act,
+                                    int act_nn, void *stream) {
+  TN_REQUIRE(a && dtop && gz && B > 0 && S > 0 && M > 0, TN_ERR_ARG, "tn_poolbwd_nhwc_bf16: bad argument");
+  TN_REQUIRE(act_is_fast(act), TN_ERR_UNSUPPORTED, "tn_poolbwd_nhwc_bf16: activation %d unsupported", act);
+  TN_REQUIRE(!pooled || S % 2 == 0, TN_ERR_SHAPE, "tn_poolbwd_nhwc_bf16: odd size %d with a 2x2 pool", S);
+  const int64_t total = (int64_t)B * S * S * M;
+  poolbwd_nhwc_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)a, (const __nv_bfloat16 *)pooled, dtop, dtop_nchw_f32,
+      (__nv_bfloat16 *)gz, total, S, M, make_actk(act, act_nn));
+  TN_LAUNCH_CHECK("tn_poolbwd_nhwc_bf16");
   return TN_OK;
 }
 

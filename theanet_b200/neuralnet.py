@@ -267,7 +267,10 @@ class NeuralNet():
         # fused small-channel kernels (conv_fused.cu)
         self.ws = {}
         self.conv_fused = {}
+        self._plan_conv_tc()
         for li, lyr in enumerate(self.tr_layers):
+            if isinstance(lyr, ConvLayer) and li in self.conv_tc:
+                continue
             if isinstance(lyr, ConvLayer):
                 nb = _C.lib.tn_conv2d_wgrad_workspace_bytes(B, lyr.num_prev_maps, lyr.in_sz,
                                                             lyr.num_maps, lyr.filter_sz)
@@ -289,6 +292,58 @@ class NeuralNet():
         self.launches = {}          # 'train' / 'test' -> kernels of this library per step
         if self.dist.world > 1:     # replicas must start identical (rank 0 wins)
             torch.distributed.broadcast(self.theta, src=0, group=self.dist.group)
+
+    # ------------------------------------------------------------------------------------------
+    # mixed-precision conv stack (training_params['CONV_DTYPE'] = 'bfloat16'; config C4)
+    # ------------------------------------------------------------------------------------------
+    def _conv_tc_ok(self, li):
+        lyr = self.tr_layers[li]
+        nxt = self.tr_layers[li + 1] if li + 1 < len(self.tr_layers) else None
+        if lyr.mode != 'same' or lyr.act.code not in (_C.ACT_LINEAR, _C.ACT_RELU, _C.ACT_LEAKY):
+            return False
+        if isinstance(nxt, PoolLayer) and (nxt.pool_sz != 2 or lyr.out_sz > 16 or nxt.ignore_border):
+            return False
+        return bool(_C.lib.tn_conv2d_tc_supported(lyr.num_prev_maps, lyr.in_sz, lyr.num_maps,
+                                                  lyr.filter_sz, lyr.out_sz))
+
+    def _plan_conv_tc(self):
+        """conv_tc[li]: buffers of ConvLayer li (and the PoolLayer above it) on the tcgen05 bf16
+        implicit-GEMM kernels (conv_tc.cu).  Activations inside the stack are NHWC bfloat16; they
+        are converted from / to the float32 NCHW tensors of the neighbouring layers at its ends."""
+        from types import SimpleNamespace
+        self.conv_tc = {}
+        if str(self.tr_prms.get('CONV_DTYPE', 'float32')).lower() not in ('bf16', 'bfloat16'):
+            return
+        dev, B, bf = self.device, self.local_bsz, torch.bfloat16
+        L = self.tr_layers
+        for li, lyr in enumerate(L):
+            if not isinstance(lyr, ConvLayer) or not self._conv_tc_ok(li):
+                continue
+            nxt = L[li + 1] if li + 1 < len(L) else None
+            st = SimpleNamespace(pool=nxt if isinstance(nxt, PoolLayer) else None)
+            S, O, Ci, M, f = lyr.in_sz, lyr.out_sz, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz
+            # input: the bf16 output of a tensor-core block right below, or a converted copy
+            src = None
+            if (li - 1) in self.conv_tc and self.conv_tc[li - 1].pool is None:
+                src = self.conv_tc[li - 1].a
+            elif (li - 2) in self.conv_tc and self.conv_tc[li - 2].pool is L[li - 1]:
+                src = self.conv_tc[li - 2].pooled
+            st.convert_in = src is None
+            st.xin = src if src is not None else torch.empty((B, S, S, Ci), dtype=bf, device=dev)
+            st.a = torch.empty((B, O, O, M), dtype=bf, device=dev)
+            st.pooled = torch.empty((B, O // 2, O // 2, M), dtype=bf, device=dev) if st.pool else None
+            st.gz = torch.empty((B, O, O, M), dtype=bf, device=dev)
+            st.dx = torch.empty((B, S, S, Ci), dtype=bf, device=dev) if self.need_below[li] else None
+            st.Wp = torch.empty(M * f * f * Ci, dtype=bf, device=dev)
+            st.Wpd = torch.empty(M * f * f * Ci, dtype=bf, device=dev)
+            nb = _C.lib.tn_conv2d_tc_wgrad_workspace_bytes(B, Ci, M, f, O)
+            st.ws = torch.empty((nb + 3) // 4, dtype=torch.float32, device=dev)
+            st.out_idx = li + 1 if st.pool else li
+            st.convert_out = True                 # cleared below when a tensor-core conv consumes it
+            self.conv_tc[li] = st
+            if not st.convert_in:
+                below = self.conv_tc[li - 1] if (li - 1) in self.conv_tc else self.conv_tc[li - 2]
+                below.convert_out = False
 
     @staticmethod
     def _fused_conv_ok(lyr):
@@ -356,6 +411,23 @@ class NeuralNet():
                 _C.call('tn_elastic_warp', _C.ptr(corpus), idxp, ctl, B, C_, h, invert, mode, gidx,
                         gfrac, pflip, self._inj(0, 'flip') if train else None, seed, _C.ptr(out),
                         st)
+            elif isinstance(lyr, ConvLayer) and li in self.conv_tc:
+                t = self.conv_tc[li]
+                S_, O_, Ci, M_, f_ = lyr.in_sz, lyr.out_sz, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz
+                if t.convert_in:
+                    _C.call('tn_nchw_f32_to_nhwc_bf16', _C.ptr(x), _C.ptr(t.xin), B, Ci, S_, S_, st)
+                _C.call('tn_conv2d_tc_pack_weights', _C.ptr(lyr.W.tensor), _C.ptr(t.Wp), M_, Ci, f_, 0, st)
+                if train and self.need_below[li]:
+                    _C.call('tn_conv2d_tc_pack_weights', _C.ptr(lyr.W.tensor), _C.ptr(t.Wpd), M_, Ci,
+                            f_, 1, st)
+                _C.call('tn_conv2d_tc_fprop', _C.ptr(t.xin), _C.ptr(t.Wp), _C.ptr(lyr.b.tensor),
+                        _C.ptr(t.a), _C.ptr(t.pooled), B, Ci, S_, M_, f_, lyr.pad_lo, O_,
+                        lyr.act.code, lyr.act.nn, st)
+                if t.convert_out:
+                    src = t.pooled if t.pool else t.a
+                    Po = O_ // 2 if t.pool else O_
+                    _C.call('tn_nhwc_bf16_to_nchw_f32', _C.ptr(src), _C.ptr(self.out[t.out_idx]), B,
+                            M_, Po, Po, st)
             elif isinstance(lyr, ConvLayer) and li in self.conv_fused:
                 pl = self.conv_fused[li]
                 _C.call('tn_convpool_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor),
@@ -366,7 +438,9 @@ class NeuralNet():
                 _C.call('tn_conv2d_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor), _C.ptr(lyr.b.tensor),
                         _C.ptr(out), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz,
                         lyr.pad_lo, lyr.out_sz, lyr.act.code, lyr.act.nn, st)
-            elif isinstance(lyr, PoolLayer) and (li - 1) in self.conv_fused:
+            elif isinstance(lyr, PoolLayer) and ((li - 1) in self.conv_fused or
+                                                 ((li - 1) in self.conv_tc and
+                                                  self.conv_tc[li - 1].pool is not None)):
                 pass                                  # produced by the fused conv kernel below it
             elif isinstance(lyr, PoolLayer):
                 _C.call('tn_maxpool_fwd', _C.ptr(x), _C.ptr(out), B * lyr.num_maps, lyr.in_sz,
@@ -408,6 +482,7 @@ class NeuralNet():
         ctl = _C.ptr(self.ctl)
         L = self.tr_layers
         g = self.gsoft                       # dL/dz of the layer being visited
+        g_bf16 = None                        # ... or, inside the bf16 conv stack, an NHWC bf16 tensor
         for li in range(len(L) - 1, 0, -1):
             lyr = L[li]
             x = self.out[li - 1]
@@ -426,6 +501,28 @@ class NeuralNet():
                     po, ac, nn, pk, sd, mi = fuse or (None, 0, 0, 1.0, 0, None)
                     _C.call('tn_dense_bwd_data', _C.ptr(g), _C.ptr(lyr.w.tensor), _C.ptr(dx), B,
                             lyr.n_in, lyr.n_out, _C.ptr(po), ac, nn, pk, sd, ctl, mi, st)
+            elif isinstance(lyr, ConvLayer) and li in self.conv_tc:
+                t = self.conv_tc[li]
+                S_, O_, Ci, M_, f_ = lyr.in_sz, lyr.out_sz, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz
+                dtop, fmt = (g_bf16, 0) if g_bf16 is not None else (g, 1)
+                _C.call('tn_poolbwd_nhwc_bf16', _C.ptr(t.a), _C.ptr(t.pooled), _C.ptr(dtop), fmt,
+                        _C.ptr(t.gz), B, O_, M_, lyr.act.code, lyr.act.nn, st)
+                if self.trainable[li]:
+                    _C.call('tn_conv2d_tc_wgrad', _C.ptr(t.xin), _C.ptr(t.gz), _C.ptr(lyr.W.grad),
+                            _C.ptr(lyr.b.grad), _C.ptr(t.ws), B, Ci, S_, M_, f_, lyr.pad_lo, O_, st)
+                g_bf16 = None
+                if below:
+                    _C.call('tn_conv2d_tc_dgrad', _C.ptr(t.gz), _C.ptr(t.Wpd), _C.ptr(t.dx), B, Ci,
+                            S_, M_, f_, lyr.pad_lo, O_, st)
+                    if t.convert_in:
+                        _C.call('tn_nhwc_bf16_to_nchw_f32', _C.ptr(t.dx), _C.ptr(dx), B, Ci, S_, S_, st)
+                        if fuse:                      # a float32 conv directly below: its act'
+                            if fuse[3] < 1.0:
+                                raise NotImplementedError("dropout-masked output feeding a conv")
+                            _C.call('tn_act_bwd', _C.ptr(dx), _C.ptr(fuse[0]), _C.ptr(dx),
+                                    B * Ci * S_ * S_, fuse[1], fuse[2], st)
+                    else:
+                        g_bf16 = t.dx
             elif isinstance(lyr, ConvLayer) and li in self.conv_fused:
                 # g is dL/d(pooled output); the pool backward is folded into both kernels
                 pl = self.conv_fused[li]
@@ -454,7 +551,9 @@ class NeuralNet():
                             lyr.filter_sz, lyr.pad_lo, lyr.out_sz, ac, nn, st)
                     if fuse and fuse[3] < 1.0:
                         raise NotImplementedError("dropout-masked dense output feeding a conv")
-            elif isinstance(lyr, PoolLayer) and (li - 1) in self.conv_fused:
+            elif isinstance(lyr, PoolLayer) and ((li - 1) in self.conv_fused or
+                                                 ((li - 1) in self.conv_tc and
+                                                  self.conv_tc[li - 1].pool is not None)):
                 continue                              # g stays dL/d(pooled): see the conv branch
             elif isinstance(lyr, PoolLayer):
                 if below:

@@ -17,6 +17,11 @@ def st():
 
 
 def timeit(fn, reps=10):
+    if os.environ.get('TN_BENCH_PLAIN'):          # for ncu: two plain launches, no graph
+        fn()
+        fn()
+        torch.cuda.synchronize()
+        return 1.0
     fn()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
