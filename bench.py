@@ -228,8 +228,8 @@ def profile_stages(net, fn, nb, reps):
         records.setdefault((name, k), []).append((s, e))
 
     import theanet_b200.neuralnet as nnmod
-    saved = net.use_graph
-    net.use_graph = False
+    saved, saved_ov = net.use_graph, net.overlap_wgrad
+    net.use_graph, net.overlap_wgrad = False, False
     _C.call = timed_call
     nnmod._C.call = timed_call
     try:
@@ -242,7 +242,7 @@ def profile_stages(net, fn, nb, reps):
     finally:
         _C.call = orig
         nnmod._C.call = orig
-        net.use_graph = saved
+        net.use_graph, net.overlap_wgrad = saved, saved_ov
     out = {}
     for k, evs in records.items():
         ts = [s.elapsed_time(e) for s, e in evs[1:]] or [evs[0][0].elapsed_time(evs[0][1])]

@@ -490,28 +490,54 @@ __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, fl
 __global__ void poolbwd_nhwc_kernel(const __nv_bfloat16 *__restrict__ a,
                                     const __nv_bfloat16 *__restrict__ pooled,
                                     const void *__restrict__ dtop, int dtop_nchw_f32,
-                                    __nv_bfloat16 *__restrict__ gz, int64_t total, int S, int M,
-                                    ActK ak) {
-  const int P = S >> 1;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int m = (int)(t % M);
-    int64_t rr = t / M;
-    const int x = (int)(rr % S); rr /= S;
-    const int y = (int)(rr % S);
-    const int64_t b = rr / S;
-    const float av = __bfloat162float(a[t]);
-    float g = 0.f;
+                                    __nv_bfloat16 *__restrict__ gz, uint32_t total8, int S, int M,
+                                    FastDiv32 divM8, FastDiv32 divS, ActK ak) {
+  // one thread = 8 consecutive channels of one pixel (16-byte loads / stores)
+  const int P = S >> 1, M8 = M >> 3;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total8; t += gridDim.x * blockDim.x) {
+    uint32_t rr = divM8.div(t);
+    const int m0 = (int)(t - rr * M8) * 8;
+    uint32_t r2 = divS.div(rr);
+    const int x = (int)(rr - r2 * S);
+    const uint32_t b = divS.div(r2);
+    const int y = (int)(r2 - b * S);
+    const uint4 av4 = reinterpret_cast<const uint4 *>(a)[t];
+    const __nv_bfloat16 *av = reinterpret_cast<const __nv_bfloat16 *>(&av4);
+    float g[8];
+    bool hit[8];
     if (pooled) {
-      const int64_t o = ((b * P + (y >> 1)) * P + (x >> 1)) * M + m;
-      if (a[t] == pooled[o])
-        g = dtop_nchw_f32 ? reinterpret_cast<const float *>(dtop)[((b * M + m) * P + (y >> 1)) * P + (x >> 1)]
-                          : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(dtop)[o]);
+      const size_t o = (((size_t)b * P + (y >> 1)) * P + (x >> 1)) * M + m0;
+      const uint4 pv4 = *reinterpret_cast<const uint4 *>(pooled + o);
+      const __nv_bfloat16 *pv = reinterpret_cast<const __nv_bfloat16 *>(&pv4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) hit[e] = av[e] == pv[e];
+      if (dtop_nchw_f32) {
+        const float *d = reinterpret_cast<const float *>(dtop);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          g[e] = hit[e] ? d[(((size_t)b * M + m0 + e) * P + (y >> 1)) * P + (x >> 1)] : 0.f;
+      } else {
+        const uint4 dv4 = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(dtop) + o);
+        const __nv_bfloat16 *dv = reinterpret_cast<const __nv_bfloat16 *>(&dv4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) g[e] = hit[e] ? __bfloat162float(dv[e]) : 0.f;
+      }
+    } else if (dtop_nchw_f32) {
+      const float *d = reinterpret_cast<const float *>(dtop);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = d[(((size_t)b * M + m0 + e) * S + y) * S + x];
     } else {
-      g = dtop_nchw_f32 ? reinterpret_cast<const float *>(dtop)[((b * M + m) * S + y) * S + x]
-                        : __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(dtop)[t]);
+      const uint4 dv4 = reinterpret_cast<const uint4 *>(dtop)[t];
+      const __nv_bfloat16 *dv = reinterpret_cast<const __nv_bfloat16 *>(&dv4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = __bfloat162float(dv[e]);
     }
-    gz[t] = __float2bfloat16_rn(g * act_bwd_t<false>(ak, av));
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      pk[e] = pack_bf16x2(g[2 * e] * act_bwd_t<false>(ak, __bfloat162float(av[2 * e])),
+                          g[2 * e + 1] * act_bwd_t<false>(ak, __bfloat162float(av[2 * e + 1])));
+    reinterpret_cast<uint4 *>(gz)[t] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }
 }
 
@@ -650,10 +676,13 @@ extern "C" int tn_poolbwd_nhwc_bf16(const void *a, const void *pooled, const voi
   TN_REQUIRE(a && dtop && gz && B > 0 && S > 0 && M > 0, TN_ERR_ARG, "tn_poolbwd_nhwc_bf16: bad argument");
   TN_REQUIRE(act_is_fast(act), TN_ERR_UNSUPPORTED, "tn_poolbwd_nhwc_bf16: activation %d unsupported", act);
   TN_REQUIRE(!pooled || S % 2 == 0, TN_ERR_SHAPE, "tn_poolbwd_nhwc_bf16: odd size %d with a 2x2 pool", S);
-  const int64_t total = (int64_t)B * S * S * M;
-  poolbwd_nhwc_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
+  TN_REQUIRE(M % 8 == 0, TN_ERR_UNSUPPORTED, "tn_poolbwd_nhwc_bf16: needs M %% 8 == 0 (got %d)", M);
+  const int64_t total8 = (int64_t)B * S * S * (M / 8);
+  TN_REQUIRE(total8 < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_poolbwd_nhwc_bf16: tensor too large");
+  poolbwd_nhwc_kernel<<<blocks_for(total8), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)a, (const __nv_bfloat16 *)pooled, dtop, dtop_nchw_f32,
-      (__nv_bfloat16 *)gz, total, S, M, make_actk(act, act_nn));
+      (__nv_bfloat16 *)gz, (uint32_t)total8, S, M, FastDiv32(M / 8), FastDiv32(S),
+      make_actk(act, act_nn));
   TN_LAUNCH_CHECK("tn_poolbwd_nhwc_bf16");
   return TN_OK;
 }

@@ -7,41 +7,45 @@
 
 namespace tn {
 
+struct PoolGeom {
+  int S, p, O;
+  FastDiv32 divO, divS, divp;
+};
+
+// 32-bit indexing (tensors below 2^32 elements) with multiply-high divisions
 template <int P>
 __global__ void maxpool_fwd_kernel(const float *__restrict__ x, float *__restrict__ out,
-                                   int64_t total, int S, int p_rt, int O) {
-  const int p = P > 0 ? P : p_rt;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int oj = (int)(t % O);
-    const int64_t r = t / O;
-    const int oi = (int)(r % O);
-    const int64_t plane = r / O;
-    const float *src = x + plane * S * S;
+                                   uint32_t total, PoolGeom k) {
+  const int p = P > 0 ? P : k.p;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t r = k.divO.div(t);
+    const int oj = (int)(t - r * k.O);
+    const uint32_t plane = k.divO.div(r);
+    const int oi = (int)(r - plane * k.O);
+    const float *src = x + (size_t)plane * k.S * k.S;
     const int y0 = oi * p, x0 = oj * p;
-    const int y1 = min(y0 + p, S), x1 = min(x0 + p, S);
+    const int y1 = min(y0 + p, k.S), x1 = min(x0 + p, k.S);
     float m = -INFINITY;
     for (int yy = y0; yy < y1; ++yy)
-      for (int xx = x0; xx < x1; ++xx) m = fmaxf(m, src[yy * S + xx]);
+      for (int xx = x0; xx < x1; ++xx) m = fmaxf(m, src[yy * k.S + xx]);
     out[t] = m;
   }
 }
 
 __global__ void maxpool_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ x,
                                    const float *__restrict__ out, float *__restrict__ dx,
-                                   int64_t total, int S, int p, int O, int act, float act_nn) {
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-       t += (int64_t)gridDim.x * blockDim.x) {
-    const int xx = (int)(t % S);
-    const int64_t r = t / S;
-    const int yy = (int)(r % S);
-    const int64_t plane = r / S;
-    const int oi = yy / p, oj = xx / p;
+                                   uint32_t total, PoolGeom k, ActK ak) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t r = k.divS.div(t);
+    const int xx = (int)(t - r * k.S);
+    const uint32_t plane = k.divS.div(r);
+    const int yy = (int)(r - plane * k.S);
+    const int oi = (int)k.divp.div((uint32_t)yy), oj = (int)k.divp.div((uint32_t)xx);
     float g = 0.f;
-    if (oi < O && oj < O) {  // rows/cols beyond O*p exist only with ignore_border
-      const int64_t o = (plane * O + oi) * O + oj;
+    if (oi < k.O && oj < k.O) {  // rows/cols beyond O*p exist only with ignore_border
+      const size_t o = ((size_t)plane * k.O + oi) * k.O + oj;
       const float a = x[t];
-      if (a == out[o]) g = dout[o] * act_bwd_from_out(a, act, act_nn);
+      if (a == out[o]) g = dout[o] * act_bwd_k(ak, a);
     }
     dx[t] = g;
   }
@@ -57,12 +61,14 @@ extern "C" int tn_maxpool_fwd(const float *x, float *out, int planes, int S, int
   TN_REQUIRE(planes > 0 && S > 0 && p > 0 && out_sz > 0 && out_sz * p < S + p, TN_ERR_SHAPE,
              "tn_maxpool_fwd: bad shape planes=%d S=%d p=%d out=%d", planes, S, p, out_sz);
   const int64_t total = (int64_t)planes * out_sz * out_sz;
+  TN_REQUIRE((int64_t)planes * S * S < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_maxpool_fwd: tensor too large");
   const int threads = 256;
   const int blocks = (int)min64(ceil_div64(total, threads), (int64_t)kNumSM * 32);
   cudaStream_t st = (cudaStream_t)stream;
-  if (p == 2) maxpool_fwd_kernel<2><<<blocks, threads, 0, st>>>(x, out, total, S, p, out_sz);
-  else if (p == 3) maxpool_fwd_kernel<3><<<blocks, threads, 0, st>>>(x, out, total, S, p, out_sz);
-  else maxpool_fwd_kernel<0><<<blocks, threads, 0, st>>>(x, out, total, S, p, out_sz);
+  PoolGeom k{S, p, out_sz, FastDiv32(out_sz), FastDiv32(S), FastDiv32(p)};
+  if (p == 2) maxpool_fwd_kernel<2><<<blocks, threads, 0, st>>>(x, out, (uint32_t)total, k);
+  else if (p == 3) maxpool_fwd_kernel<3><<<blocks, threads, 0, st>>>(x, out, (uint32_t)total, k);
+  else maxpool_fwd_kernel<0><<<blocks, threads, 0, st>>>(x, out, (uint32_t)total, k);
   TN_LAUNCH_CHECK("tn_maxpool_fwd");
   return TN_OK;
 }
@@ -74,10 +80,12 @@ extern "C" int tn_maxpool_bwd(const float *dout, const float *x, const float *ou
   TN_REQUIRE(planes > 0 && S > 0 && p > 0 && out_sz > 0 && out_sz * p < S + p, TN_ERR_SHAPE,
              "tn_maxpool_bwd: bad shape");
   const int64_t total = (int64_t)planes * S * S;
+  TN_REQUIRE(total < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_maxpool_bwd: tensor too large");
   const int threads = 256;
   const int blocks = (int)min64(ceil_div64(total, threads), (int64_t)kNumSM * 32);
-  maxpool_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(dout, x, out, dx, total, S, p,
-                                                                   out_sz, act, (float)act_nn);
+  PoolGeom k{S, p, out_sz, FastDiv32(out_sz), FastDiv32(S), FastDiv32(p)};
+  maxpool_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      dout, x, out, dx, (uint32_t)total, k, make_actk(act, act_nn));
   TN_LAUNCH_CHECK("tn_maxpool_bwd");
   return TN_OK;
 }

@@ -16,6 +16,7 @@ PyTorch is used for device memory, streams, CUDA graphs and torch.distributed on
 """
 import ctypes
 import os
+from contextlib import contextmanager
 from functools import reduce
 from operator import mul
 
@@ -108,6 +109,8 @@ class NeuralNet():
         self.fuse_conv = fuse_conv
         self.fuse_head = fuse_head
         self.nccl_in_graph = os.environ.get('TN_GRAPH_NCCL', '0') == '1'
+        self.overlap_wgrad = os.environ.get('TN_OVERLAP_WGRAD', '1') == '1'
+        self._side = None
 
         # Input Layer
         input_layer_type = getattr(layer, layers[0][0])
@@ -476,6 +479,29 @@ class NeuralNet():
             return (self.out[li], lyr.act.code, lyr.act.nn, 1.0, 0, None)
         return None
 
+    @contextmanager
+    def _wgrad_stream(self):
+        """Weight-gradient kernels do not feed the rest of the backward pass: they are forked
+        onto side streams (graph branches once captured) and joined before the update, so that
+        e.g. the dW GEMM overlaps the dX GEMM and the conv wgrad overlaps the conv dgrad."""
+        if not self.overlap_wgrad:
+            yield self._stream()
+            return
+        if self._side is None:
+            self._side = [torch.cuda.Stream(self.device) for _ in range(2)]
+            self._side_rr = 0
+        side = self._side[self._side_rr]
+        self._side_rr ^= 1
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            yield ctypes.c_void_p(side.cuda_stream)
+
+    def _join_wgrad(self):
+        if self.overlap_wgrad and self._side is not None:
+            main = torch.cuda.current_stream(self.device)
+            for side in self._side:
+                main.wait_stream(side)
+
     def _backward(self):
         st = self._stream()
         B = self.local_bsz
@@ -491,12 +517,15 @@ class NeuralNet():
             fuse = self._fuse_info(li - 1) if below else None
             if self.head and li == len(L) - 1:
                 # dL/dz of the layer below was already produced by tn_softmax_head_fwd_bwd
-                _C.call('tn_softmax_head_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
-                        _C.ptr(lyr.b.grad), _C.ptr(self.ws_head), B, lyr.n_in, lyr.n_out, st)
+                with self._wgrad_stream() as sw:
+                    _C.call('tn_softmax_head_bwd_weights', _C.ptr(x), _C.ptr(g),
+                            _C.ptr(lyr.w.grad), _C.ptr(lyr.b.grad), _C.ptr(self.ws_head), B,
+                            lyr.n_in, lyr.n_out, sw)
             elif isinstance(lyr, HiddenLayer):
                 if self.trainable[li]:
-                    _C.call('tn_dense_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
-                            _C.ptr(lyr.b.grad), B, lyr.n_in, lyr.n_out, st)
+                    with self._wgrad_stream() as sw:
+                        _C.call('tn_dense_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
+                                _C.ptr(lyr.b.grad), B, lyr.n_in, lyr.n_out, sw)
                 if below:
                     po, ac, nn, pk, sd, mi = fuse or (None, 0, 0, 1.0, 0, None)
                     _C.call('tn_dense_bwd_data', _C.ptr(g), _C.ptr(lyr.w.tensor), _C.ptr(dx), B,
@@ -508,8 +537,10 @@ class NeuralNet():
                 _C.call('tn_poolbwd_nhwc_bf16', _C.ptr(t.a), _C.ptr(t.pooled), _C.ptr(dtop), fmt,
                         _C.ptr(t.gz), B, O_, M_, lyr.act.code, lyr.act.nn, st)
                 if self.trainable[li]:
-                    _C.call('tn_conv2d_tc_wgrad', _C.ptr(t.xin), _C.ptr(t.gz), _C.ptr(lyr.W.grad),
-                            _C.ptr(lyr.b.grad), _C.ptr(t.ws), B, Ci, S_, M_, f_, lyr.pad_lo, O_, st)
+                    with self._wgrad_stream() as sw:
+                        _C.call('tn_conv2d_tc_wgrad', _C.ptr(t.xin), _C.ptr(t.gz),
+                                _C.ptr(lyr.W.grad), _C.ptr(lyr.b.grad), _C.ptr(t.ws), B, Ci, S_, M_,
+                                f_, lyr.pad_lo, O_, sw)
                 g_bf16 = None
                 if below:
                     _C.call('tn_conv2d_tc_dgrad', _C.ptr(t.gz), _C.ptr(t.Wpd), _C.ptr(t.dx), B, Ci,
@@ -529,9 +560,10 @@ class NeuralNet():
                 geom = (B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
                         lyr.out_sz, lyr.act.code, lyr.act.nn, pl.pool_sz, pl.out_sz)
                 if self.trainable[li]:
-                    _C.call('tn_convpool_bwd_weights', _C.ptr(x), _C.ptr(self.out[li]),
-                            _C.ptr(self.out[li + 1]), _C.ptr(g), _C.ptr(lyr.W.grad),
-                            _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), *geom, st)
+                    with self._wgrad_stream() as sw:
+                        _C.call('tn_convpool_bwd_weights', _C.ptr(x), _C.ptr(self.out[li]),
+                                _C.ptr(self.out[li + 1]), _C.ptr(g), _C.ptr(lyr.W.grad),
+                                _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), *geom, sw)
                 if below:
                     if fuse and fuse[3] < 1.0:
                         raise NotImplementedError("dropout-masked dense output feeding a conv")
@@ -541,9 +573,10 @@ class NeuralNet():
                             st)
             elif isinstance(lyr, ConvLayer):
                 if self.trainable[li]:
-                    _C.call('tn_conv2d_wgrad', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.W.grad),
-                            _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), B, lyr.num_prev_maps,
-                            lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo, lyr.out_sz, st)
+                    with self._wgrad_stream() as sw:
+                        _C.call('tn_conv2d_wgrad', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.W.grad),
+                                _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), B, lyr.num_prev_maps,
+                                lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo, lyr.out_sz, sw)
                 if below:
                     po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, 0, 0)
                     _C.call('tn_conv2d_dgrad', _C.ptr(g), _C.ptr(lyr.W.tensor), _C.ptr(dx),
@@ -614,6 +647,7 @@ class NeuralNet():
                     _C.ptr(self.ctl), B, n_out, 1.0 / self.batch_sz, _C.ptr(self.logprob),
                     _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
         self._backward()
+        self._join_wgrad()
         _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
         if self.dist.world > 1 and not self.nccl_in_graph:
             return                                   # the caller reduces, then _update_launches

@@ -19,20 +19,32 @@ def main():
     ap.add_argument('--img', type=int, default=28)
     ap.add_argument('--maps', type=int, default=1)
     ap.add_argument('--classes', type=int, default=10)
+    ap.add_argument('--bf16', type=int, default=0)
+    ap.add_argument('--graph', type=int, default=0)
     a = ap.parse_args()
     from theanet_b200.neuralnet import NeuralNet
     with open(os.path.join(ROOT, 'params', a.prms)) as f:
         p = ast.literal_eval(f.read())
     p['training_params'].update(SEED=555555, BATCH_SZ=a.batch)
+    if a.bf16:
+        p['training_params']['CONV_DTYPE'] = 'bfloat16'
     p['layers'][0][1]['img_sz'] = a.img
     rng = np.random.default_rng(1234)
     x = rng.random((a.batch * 4, a.maps, a.img, a.img), dtype=np.float32)
     x *= (x > .8)
     y = rng.integers(0, a.classes, a.batch * 4).astype(np.int32)
-    net = NeuralNet(p['layers'], p['training_params'], use_graph=False)
+    net = NeuralNet(p['layers'], p['training_params'], use_graph=bool(a.graph))
     fn = net.get_trin_model(x, y)
+    import time
+    import torch
     for s in range(a.steps):
         cost, _, _ = fn(s % 4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        cost, _, _ = fn(s % 4)
+    torch.cuda.synchronize()
+    print('ms/step (host-timed, incl. sync + D2H)', 1e3 * (time.perf_counter() - t0) / a.steps)
     print('cost', float(cost), 'launches/step', net.launches.get('train'))
 
 
