@@ -160,6 +160,17 @@ int tn_conv2d_tc_fprop(const void *x, const void *Wp, const float *bias, void *a
 /* dx (B,S,S,C) bf16 from gz (B,out,out,M) bf16 */
 int tn_conv2d_tc_dgrad(const void *gz, const void *Wp_dgrad, void *dx, int B, int C, int S, int M,
                        int f, int pad_lo, int out_sz, void *stream);
+/* First layer with few input channels (C*f*f <= 64): xcol (B,S,S,64) bf16 with
+ * xcol[..,k] = xpad[c, y+u-pad, x+v-pad], k = (c*f+u)*f+v; the layer then runs as a 1x1
+ * tensor-core convolution over 64 "channels" (tn_conv2d_tc_fprop / _wgrad with f = 1, C = 64)
+ * with filters packed by tn_conv2d_tc_pack_weights_im2col ([M][64]) and the float32 [M][64]
+ * weight gradient scattered back to OIHW by tn_conv2d_tc_unpack_wgrad_im2col. */
+int tn_im2col_bf16(const float *x, void *xcol, int B, int C, int S, int f, int pad_lo, void *stream);
+int tn_conv2d_tc_pack_weights_im2col(const float *W, void *Wcol, int M, int C, int f, void *stream);
+int tn_conv2d_tc_unpack_wgrad_im2col(const float *dWcol, float *dW, int M, int C, int f,
+                                     void *stream);
+/* 2x2 max-pool of an NHWC bf16 tensor (B,S,S,M) -> (B,S/2,S/2,M) */
+int tn_maxpool2_nhwc_bf16(const void *a, void *pooled, int B, int S, int M, void *stream);
 /* gz = [a == pooled(2x2 window)] * dtop * act'(a), NHWC bf16 (every tied maximum receives the
  * gradient).  dtop: float32 NCHW (B,M,S/2,S/2) if dtop_nchw_f32 else bf16 NHWC; pooled == NULL:
  * no pool layer, dtop has the shape of a. */

@@ -364,15 +364,18 @@ def bf16_round(a):
     return r.view(np.float32).reshape(np.shape(a))
 
 
-def conv_tc_eligible(in_maps, in_sz, M, f, mode, actvn, out_sz, pool_sz=None, ignore_border=False):
+def conv_tc_eligible(in_maps, in_sz, M, f, mode, actvn, out_sz, pool_sz=None, ignore_border=False,
+                     first=False):
     """Which ConvLayers theanet_b200 runs as bf16 tensor-core implicit GEMMs when
-    training_params['CONV_DTYPE'] == 'bfloat16' (mirrors NeuralNet._conv_tc_ok)."""
+    training_params['CONV_DTYPE'] == 'bfloat16' (mirrors NeuralNet._conv_tc_kind): wide layers
+    directly, the first weighted layer through a 64-wide im2col when C*f*f <= 64."""
     fast = actvn in ('linear', 'relu') or (len(actvn) == 6 and actvn.startswith('relu'))
-    if not (in_maps % 64 == 0 and M % 64 == 0 and mode == 'same' and fast and 1 <= f <= 7):
+    wide = in_maps % 64 == 0 or (first and in_maps * f * f <= 64)
+    if not (wide and M % 64 == 0 and mode == 'same' and fast and 1 <= f <= 7):
         return False
     if out_sz < 4 or out_sz > 128 or out_sz & (out_sz - 1):
         return False
-    if pool_sz is not None and (pool_sz != 2 or out_sz > 16 or ignore_border):
+    if pool_sz is not None and (pool_sz != 2 or out_sz % 2 or ignore_border):
         return False
     return True
 
@@ -476,7 +479,8 @@ class OracleNet:
                 L['tc'] = conv_tc_eligible(
                     L['in_maps'], in_sz, L['num_maps'], L['args']['filter_sz'], L['mode'], L['actvn'],
                     L['out_sz'], pool['pool_sz'] if pool else None,
-                    pool.get('ignore_border', False) if pool else False)
+                    pool.get('ignore_border', False) if pool else False,
+                    first=not any(P['params'] for P in self.spec[:li]))
         if 'CUR_EPOCH' not in training_params:                               # neuralnet.py:108-109
             training_params['CUR_EPOCH'] = 0
         self.set_rate()

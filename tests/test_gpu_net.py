@@ -255,9 +255,10 @@ def test_cifar3conv_bf16_tensor_core_stack_matches_oracle():
     x, y = synth(2 * B, 3, 32, 10, dense=True)
     p1, p2 = copy.deepcopy(prms), copy.deepcopy(prms)
     net = NeuralNet(p1['layers'], p1['training_params'])
-    assert sorted(net.conv_tc) == [3, 5]              # conv 2 and conv 3 on tcgen05, conv 1 direct
+    assert sorted(net.conv_tc) == [1, 3, 5]           # all three convs on tcgen05 (conv 1 via im2col)
+    assert net.conv_tc[1].im2col and not net.conv_tc[1].fuse_pool and net.conv_tc[3].fuse_pool
     on = O.OracleNet(p2['layers'], p2['training_params'])
-    assert [L['tc'] for L in on.spec if L['kind'] == 'ConvLayer'] == [False, True, True]
+    assert [L['tc'] for L in on.spec if L['kind'] == 'ConvLayer'] == [True, True, True]
     fn = net.get_trin_model(x, y)
     for s in range(3):
         i = s % 2

@@ -61,6 +61,10 @@ SIGNATURES = {
     'tn_conv2d_tc_pack_weights': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_conv2d_tc_fprop': (_I, [_P] * 5 + [_I] * 9 + [_P]),
     'tn_conv2d_tc_dgrad': (_I, [_P] * 3 + [_I] * 7 + [_P]),
+    'tn_im2col_bf16': (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    'tn_conv2d_tc_pack_weights_im2col': (_I, [_P, _P, _I, _I, _I, _P]),
+    'tn_conv2d_tc_unpack_wgrad_im2col': (_I, [_P, _P, _I, _I, _I, _P]),
+    'tn_maxpool2_nhwc_bf16': (_I, [_P, _P, _I, _I, _I, _P]),
     'tn_poolbwd_nhwc_bf16': (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _P]),
     'tn_conv2d_tc_wgrad_workspace_bytes': (C.c_size_t, [_I] * 5),
     'tn_conv2d_tc_wgrad': (_I, [_P] * 5 + [_I] * 7 + [_P]),

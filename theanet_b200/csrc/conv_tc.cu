@@ -483,6 +483,84 @@ __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, fl
   }
 }
 
+// ---- first layer (few input channels): im2col to 64-wide bf16 rows, then a 1x1 tensor-core conv --
+// xcol[b,y,x,k] = xpad[b, c, y+u-pad, x+v-pad] for k = (c*f+u)*f+v < C*f*f, 0 for the padding up to 64
+__global__ void im2col_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ xcol,
+                                   uint32_t total8, int C, int S, int f, int pad, FastDiv32 divS) {
+  // one thread = 8 consecutive k of one pixel
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total8; t += gridDim.x * blockDim.x) {
+    const int k0 = (int)(t & 7) * 8;
+    uint32_t rr = t >> 3;
+    uint32_t r2 = divS.div(rr);
+    const int xx = (int)(rr - r2 * S);
+    const uint32_t b = divS.div(r2);
+    const int yy = (int)(r2 - b * S);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + e;
+      v[e] = 0.f;
+      if (k < C * f * f) {
+        const int c = k / (f * f), uv = k - c * f * f;
+        const int u = uv / f, vv = uv - u * f;
+        const int y = yy + u - pad, x2 = xx + vv - pad;
+        if (y >= 0 && y < S && x2 >= 0 && x2 < S) v[e] = x[(((size_t)b * C + c) * S + y) * S + x2];
+      }
+    }
+    reinterpret_cast<uint4 *>(xcol)[t] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+// Wcol[m][k] = W[m][c][f-1-u][f-1-v] (k as above), zero padded to 64
+__global__ void pack_weights_im2col_kernel(const float *__restrict__ W, __nv_bfloat16 *__restrict__ Wc,
+                                           int M, int C, int f) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M * 64) return;
+  const int m = t >> 6, k = t & 63;
+  float v = 0.f;
+  if (k < C * f * f) {
+    const int c = k / (f * f), uv = k - c * f * f;
+    const int u = uv / f, vv = uv - u * f;
+    v = W[((m * C + c) * f + (f - 1 - u)) * f + (f - 1 - vv)];
+  }
+  Wc[t] = __float2bfloat16_rn(v);
+}
+// dW[m][c][f-1-u][f-1-v] = dWcol[m][k]
+__global__ void unpack_wgrad_im2col_kernel(const float *__restrict__ dWc, float *__restrict__ dW,
+                                           int M, int C, int f) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int K = C * f * f;
+  if (t >= M * K) return;
+  const int m = t / K, k = t - m * K;
+  const int c = k / (f * f), uv = k - c * f * f;
+  const int u = uv / f, vv = uv - u * f;
+  dW[((m * C + c) * f + (f - 1 - u)) * f + (f - 1 - vv)] = dWc[m * 64 + k];
+}
+// 2x2 max-pool of an NHWC bf16 tensor (for outputs too wide for the fused epilogue pool)
+__global__ void maxpool2_nhwc_kernel(const __nv_bfloat16 *__restrict__ a, __nv_bfloat16 *__restrict__ p,
+                                     uint32_t total8, int S, int M, FastDiv32 divM8, FastDiv32 divP) {
+  const int P = S >> 1, M8 = M >> 3;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total8; t += gridDim.x * blockDim.x) {
+    uint32_t rr = divM8.div(t);
+    const int m8 = (int)(t - rr * M8);
+    uint32_t r2 = divP.div(rr);
+    const int ox = (int)(rr - r2 * P);
+    const uint32_t b = divP.div(r2);
+    const int oy = (int)(r2 - b * P);
+    const uint4 *src = reinterpret_cast<const uint4 *>(a) + (((size_t)b * S + 2 * oy) * S + 2 * ox) * M8 + m8;
+    uint4 q[4] = {src[0], src[M8], src[(size_t)S * M8], src[(size_t)S * M8 + M8]};
+    uint4 r = q[0];
+    __nv_bfloat162 *rv = reinterpret_cast<__nv_bfloat162 *>(&r);
+#pragma unroll
+    for (int w = 1; w < 4; ++w) {
+      const __nv_bfloat162 *qv = reinterpret_cast<const __nv_bfloat162 *>(&q[w]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) rv[e] = __hmax2(rv[e], qv[e]);
+    }
+    reinterpret_cast<uint4 *>(p)[t] = r;
+  }
+}
+
 // gz[b,y,x,m] = [a == pooled(window)] * dtop(window) * act'(a)   (2x2 windows, NHWC bf16 a / pooled;
 // every tied maximum receives the gradient, as Theano's MaxPoolGrad).  dtop is either float32 NCHW
 // (B, M, P, P) -- the gradient arriving from a dense layer -- or bf16 NHWC (B, P, P, M) -- the dx of
@@ -667,6 +745,47 @@ extern "C" int tn_nhwc_bf16_to_nchw_f32(const void *x, float *y, int B, int C, i
   nhwc_bf16_to_nchw_kernel<<<blocks_for(total), 256, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16 *)x, y, total, C, H * W);
   TN_LAUNCH_CHECK("tn_nhwc_bf16_to_nchw_f32");
+  return TN_OK;
+}
+
+extern "C" int tn_im2col_bf16(const float *x, void *xcol, int B, int C, int S, int f, int pad_lo,
+                              void *stream) {
+  TN_REQUIRE(x && xcol && B > 0 && C > 0 && S > 0 && f > 0, TN_ERR_ARG, "tn_im2col_bf16: bad argument");
+  TN_REQUIRE(C * f * f <= 64, TN_ERR_UNSUPPORTED, "tn_im2col_bf16: C*f*f = %d exceeds 64", C * f * f);
+  const int64_t total8 = (int64_t)B * S * S * 8;
+  TN_REQUIRE(total8 < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_im2col_bf16: tensor too large");
+  im2col_bf16_kernel<<<blocks_for(total8), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16 *)xcol, (uint32_t)total8, C, S, f, pad_lo, FastDiv32(S));
+  TN_LAUNCH_CHECK("tn_im2col_bf16");
+  return TN_OK;
+}
+
+extern "C" int tn_conv2d_tc_pack_weights_im2col(const float *W, void *Wcol, int M, int C, int f,
+                                                void *stream) {
+  TN_REQUIRE(W && Wcol && M > 0 && C * f * f <= 64, TN_ERR_ARG, "tn_conv2d_tc_pack_weights_im2col: bad argument");
+  pack_weights_im2col_kernel<<<ceil_div(M * 64, 256), 256, 0, (cudaStream_t)stream>>>(
+      W, (__nv_bfloat16 *)Wcol, M, C, f);
+  TN_LAUNCH_CHECK("tn_conv2d_tc_pack_weights_im2col");
+  return TN_OK;
+}
+
+extern "C" int tn_conv2d_tc_unpack_wgrad_im2col(const float *dWcol, float *dW, int M, int C, int f,
+                                                void *stream) {
+  TN_REQUIRE(dWcol && dW && M > 0 && C * f * f <= 64, TN_ERR_ARG, "tn_conv2d_tc_unpack_wgrad_im2col: bad argument");
+  unpack_wgrad_im2col_kernel<<<ceil_div(M * C * f * f, 256), 256, 0, (cudaStream_t)stream>>>(dWcol, dW, M, C, f);
+  TN_LAUNCH_CHECK("tn_conv2d_tc_unpack_wgrad_im2col");
+  return TN_OK;
+}
+
+extern "C" int tn_maxpool2_nhwc_bf16(const void *a, void *pooled, int B, int S, int M, void *stream) {
+  TN_REQUIRE(a && pooled && B > 0 && S > 0 && S % 2 == 0 && M > 0 && M % 8 == 0, TN_ERR_ARG,
+             "tn_maxpool2_nhwc_bf16: bad argument");
+  const int64_t total8 = (int64_t)B * (S / 2) * (S / 2) * (M / 8);
+  TN_REQUIRE(total8 < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_maxpool2_nhwc_bf16: tensor too large");
+  maxpool2_nhwc_kernel<<<blocks_for(total8), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16 *)a, (__nv_bfloat16 *)pooled, (uint32_t)total8, S, M, FastDiv32(M / 8),
+      FastDiv32(S / 2));
+  TN_LAUNCH_CHECK("tn_maxpool2_nhwc_bf16");
   return TN_OK;
 }
 

@@ -299,15 +299,20 @@ class NeuralNet():
     # ------------------------------------------------------------------------------------------
     # mixed-precision conv stack (training_params['CONV_DTYPE'] = 'bfloat16'; config C4)
     # ------------------------------------------------------------------------------------------
-    def _conv_tc_ok(self, li):
+    def _conv_tc_kind(self, li):
+        """'tc' (wide layer, direct), 'im2col' (first weighted layer with C*f*f <= 64) or None."""
         lyr = self.tr_layers[li]
         nxt = self.tr_layers[li + 1] if li + 1 < len(self.tr_layers) else None
         if lyr.mode != 'same' or lyr.act.code not in (_C.ACT_LINEAR, _C.ACT_RELU, _C.ACT_LEAKY):
-            return False
-        if isinstance(nxt, PoolLayer) and (nxt.pool_sz != 2 or lyr.out_sz > 16 or nxt.ignore_border):
-            return False
-        return bool(_C.lib.tn_conv2d_tc_supported(lyr.num_prev_maps, lyr.in_sz, lyr.num_maps,
-                                                  lyr.filter_sz, lyr.out_sz))
+            return None
+        if isinstance(nxt, PoolLayer) and (nxt.pool_sz != 2 or lyr.out_sz % 2 or nxt.ignore_border):
+            return None
+        C_, S, M, f, O = lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.out_sz
+        if _C.lib.tn_conv2d_tc_supported(C_, S, M, f, O):
+            return 'tc'
+        if not self.need_below[li] and C_ * f * f <= 64 and _C.lib.tn_conv2d_tc_supported(64, S, M, 1, O):
+            return 'im2col'
+        return None
 
     def _plan_conv_tc(self):
         """conv_tc[li]: buffers of ConvLayer li (and the PoolLayer above it) on the tcgen05 bf16
@@ -320,31 +325,39 @@ class NeuralNet():
         dev, B, bf = self.device, self.local_bsz, torch.bfloat16
         L = self.tr_layers
         for li, lyr in enumerate(L):
-            if not isinstance(lyr, ConvLayer) or not self._conv_tc_ok(li):
+            kind = self._conv_tc_kind(li) if isinstance(lyr, ConvLayer) else None
+            if kind is None:
                 continue
             nxt = L[li + 1] if li + 1 < len(L) else None
-            st = SimpleNamespace(pool=nxt if isinstance(nxt, PoolLayer) else None)
+            st = SimpleNamespace(pool=nxt if isinstance(nxt, PoolLayer) else None,
+                                 im2col=kind == 'im2col')
             S, O, Ci, M, f = lyr.in_sz, lyr.out_sz, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz
-            # input: the bf16 output of a tensor-core block right below, or a converted copy
+            st.fuse_pool = st.pool is not None and O <= 16     # else a separate NHWC pool kernel
+            # input: the bf16 output of a tensor-core block right below, a converted copy, or the
+            # 64-wide im2col of a narrow first layer
             src = None
-            if (li - 1) in self.conv_tc and self.conv_tc[li - 1].pool is None:
-                src = self.conv_tc[li - 1].a
-            elif (li - 2) in self.conv_tc and self.conv_tc[li - 2].pool is L[li - 1]:
-                src = self.conv_tc[li - 2].pooled
-            st.convert_in = src is None
-            st.xin = src if src is not None else torch.empty((B, S, S, Ci), dtype=bf, device=dev)
+            if not st.im2col:
+                if (li - 1) in self.conv_tc and self.conv_tc[li - 1].pool is None:
+                    src = self.conv_tc[li - 1].a
+                elif (li - 2) in self.conv_tc and self.conv_tc[li - 2].pool is L[li - 1]:
+                    src = self.conv_tc[li - 2].pooled
+            st.convert_in = src is None and not st.im2col
+            Cx = 64 if st.im2col else Ci
+            st.xin = src if src is not None else torch.empty((B, S, S, Cx), dtype=bf, device=dev)
             st.a = torch.empty((B, O, O, M), dtype=bf, device=dev)
             st.pooled = torch.empty((B, O // 2, O // 2, M), dtype=bf, device=dev) if st.pool else None
             st.gz = torch.empty((B, O, O, M), dtype=bf, device=dev)
             st.dx = torch.empty((B, S, S, Ci), dtype=bf, device=dev) if self.need_below[li] else None
-            st.Wp = torch.empty(M * f * f * Ci, dtype=bf, device=dev)
-            st.Wpd = torch.empty(M * f * f * Ci, dtype=bf, device=dev)
-            nb = _C.lib.tn_conv2d_tc_wgrad_workspace_bytes(B, Ci, M, f, O)
+            nW = M * 64 if st.im2col else M * f * f * Ci
+            st.Wp = torch.empty(nW, dtype=bf, device=dev)
+            st.Wpd = torch.empty(nW, dtype=bf, device=dev)
+            st.dWcol = torch.empty(M * 64, dtype=torch.float32, device=dev) if st.im2col else None
+            nb = _C.lib.tn_conv2d_tc_wgrad_workspace_bytes(B, Cx, M, 1 if st.im2col else f, O)
             st.ws = torch.empty((nb + 3) // 4, dtype=torch.float32, device=dev)
             st.out_idx = li + 1 if st.pool else li
             st.convert_out = True                 # cleared below when a tensor-core conv consumes it
             self.conv_tc[li] = st
-            if not st.convert_in:
+            if src is not None:
                 below = self.conv_tc[li - 1] if (li - 1) in self.conv_tc else self.conv_tc[li - 2]
                 below.convert_out = False
 
@@ -417,15 +430,26 @@ class NeuralNet():
             elif isinstance(lyr, ConvLayer) and li in self.conv_tc:
                 t = self.conv_tc[li]
                 S_, O_, Ci, M_, f_ = lyr.in_sz, lyr.out_sz, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz
-                if t.convert_in:
-                    _C.call('tn_nchw_f32_to_nhwc_bf16', _C.ptr(x), _C.ptr(t.xin), B, Ci, S_, S_, st)
-                _C.call('tn_conv2d_tc_pack_weights', _C.ptr(lyr.W.tensor), _C.ptr(t.Wp), M_, Ci, f_, 0, st)
-                if train and self.need_below[li]:
-                    _C.call('tn_conv2d_tc_pack_weights', _C.ptr(lyr.W.tensor), _C.ptr(t.Wpd), M_, Ci,
-                            f_, 1, st)
-                _C.call('tn_conv2d_tc_fprop', _C.ptr(t.xin), _C.ptr(t.Wp), _C.ptr(lyr.b.tensor),
-                        _C.ptr(t.a), _C.ptr(t.pooled), B, Ci, S_, M_, f_, lyr.pad_lo, O_,
-                        lyr.act.code, lyr.act.nn, st)
+                fp = _C.ptr(t.pooled) if t.fuse_pool else None
+                if t.im2col:
+                    _C.call('tn_im2col_bf16', _C.ptr(x), _C.ptr(t.xin), B, Ci, S_, f_, lyr.pad_lo, st)
+                    _C.call('tn_conv2d_tc_pack_weights_im2col', _C.ptr(lyr.W.tensor), _C.ptr(t.Wp),
+                            M_, Ci, f_, st)
+                    _C.call('tn_conv2d_tc_fprop', _C.ptr(t.xin), _C.ptr(t.Wp), _C.ptr(lyr.b.tensor),
+                            _C.ptr(t.a), fp, B, 64, S_, M_, 1, 0, O_, lyr.act.code, lyr.act.nn, st)
+                else:
+                    if t.convert_in:
+                        _C.call('tn_nchw_f32_to_nhwc_bf16', _C.ptr(x), _C.ptr(t.xin), B, Ci, S_, S_, st)
+                    _C.call('tn_conv2d_tc_pack_weights', _C.ptr(lyr.W.tensor), _C.ptr(t.Wp), M_, Ci,
+                            f_, 0, st)
+                    if train and self.need_below[li]:
+                        _C.call('tn_conv2d_tc_pack_weights', _C.ptr(lyr.W.tensor), _C.ptr(t.Wpd), M_,
+                                Ci, f_, 1, st)
+                    _C.call('tn_conv2d_tc_fprop', _C.ptr(t.xin), _C.ptr(t.Wp), _C.ptr(lyr.b.tensor),
+                            _C.ptr(t.a), fp, B, Ci, S_, M_, f_, lyr.pad_lo, O_, lyr.act.code,
+                            lyr.act.nn, st)
+                if t.pool is not None and not t.fuse_pool:
+                    _C.call('tn_maxpool2_nhwc_bf16', _C.ptr(t.a), _C.ptr(t.pooled), B, O_, M_, st)
                 if t.convert_out:
                     src = t.pooled if t.pool else t.a
                     Po = O_ // 2 if t.pool else O_
@@ -538,9 +562,16 @@ class NeuralNet():
                         _C.ptr(t.gz), B, O_, M_, lyr.act.code, lyr.act.nn, st)
                 if self.trainable[li]:
                     with self._wgrad_stream() as sw:
-                        _C.call('tn_conv2d_tc_wgrad', _C.ptr(t.xin), _C.ptr(t.gz),
-                                _C.ptr(lyr.W.grad), _C.ptr(lyr.b.grad), _C.ptr(t.ws), B, Ci, S_, M_,
-                                f_, lyr.pad_lo, O_, sw)
+                        if t.im2col:
+                            _C.call('tn_conv2d_tc_wgrad', _C.ptr(t.xin), _C.ptr(t.gz),
+                                    _C.ptr(t.dWcol), _C.ptr(lyr.b.grad), _C.ptr(t.ws), B, 64, S_, M_,
+                                    1, 0, O_, sw)
+                            _C.call('tn_conv2d_tc_unpack_wgrad_im2col', _C.ptr(t.dWcol),
+                                    _C.ptr(lyr.W.grad), M_, Ci, f_, sw)
+                        else:
+                            _C.call('tn_conv2d_tc_wgrad', _C.ptr(t.xin), _C.ptr(t.gz),
+                                    _C.ptr(lyr.W.grad), _C.ptr(lyr.b.grad), _C.ptr(t.ws), B, Ci, S_,
+                                    M_, f_, lyr.pad_lo, O_, sw)
                 g_bf16 = None
                 if below:
                     _C.call('tn_conv2d_tc_dgrad', _C.ptr(t.gz), _C.ptr(t.Wpd), _C.ptr(t.dx), B, Ci,
