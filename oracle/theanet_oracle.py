@@ -370,7 +370,7 @@ def conv_tc_eligible(in_maps, in_sz, M, f, mode, actvn, out_sz, pool_sz=None, ig
     training_params['CONV_DTYPE'] == 'bfloat16' (mirrors NeuralNet._conv_tc_kind): wide layers
     directly, the first weighted layer through a 64-wide im2col when C*f*f <= 64."""
     fast = actvn in ('linear', 'relu') or (len(actvn) == 6 and actvn.startswith('relu'))
-    wide = in_maps % 64 == 0 or (first and in_maps * f * f <= 64)
+    wide = in_maps % 64 == 0 or (first and f == 3 and in_maps <= 7)
     if not (wide and M % 64 == 0 and mode == 'same' and fast and 1 <= f <= 7):
         return False
     if out_sz < 4 or out_sz > 128 or out_sz & (out_sz - 1):

@@ -485,30 +485,40 @@ __global__ void nhwc_bf16_to_nchw_kernel(const __nv_bfloat16 *__restrict__ x, fl
 
 // ---- first layer (few input channels): im2col to 64-wide bf16 rows, then a 1x1 tensor-core conv --
 // xcol[b,y,x,k] = xpad[b, c, y+u-pad, x+v-pad] for k = (c*f+u)*f+v < C*f*f, 0 for the padding up to 64
+template <int F>
 __global__ void im2col_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ xcol,
-                                   uint32_t total8, int C, int S, int f, int pad, FastDiv32 divS) {
-  // one thread = 8 consecutive k of one pixel
-  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total8; t += gridDim.x * blockDim.x) {
-    const int k0 = (int)(t & 7) * 8;
-    uint32_t rr = t >> 3;
-    uint32_t r2 = divS.div(rr);
-    const int xx = (int)(rr - r2 * S);
+                                   uint32_t npix, int C, int S, int f_rt, int pad, FastDiv32 divS) {
+  // one thread = one pixel: C*f*f coalesced loads (threads run along x), one 128-byte row out
+  (void)f_rt;
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < npix; t += gridDim.x * blockDim.x) {
+    const uint32_t r2 = divS.div(t);
+    const int xx = (int)(t - r2 * S);
     const uint32_t b = divS.div(r2);
     const int yy = (int)(r2 - b * S);
-    float v[8];
+    float v[64];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = k0 + e;
-      v[e] = 0.f;
-      if (k < C * f * f) {
-        const int c = k / (f * f), uv = k - c * f * f;
-        const int u = uv / f, vv = uv - u * f;
-        const int y = yy + u - pad, x2 = xx + vv - pad;
-        if (y >= 0 && y < S && x2 >= 0 && x2 < S) v[e] = x[(((size_t)b * C + c) * S + y) * S + x2];
+    for (int k = 0; k < 64; ++k) v[k] = 0.f;
+    const float *img = x + (size_t)b * C * S * S;
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {      // compile-time k keeps v[] in registers
+      if (c < C) {
+#pragma unroll
+        for (int u = 0; u < F; ++u) {
+          const int y = yy + u - pad;
+#pragma unroll
+          for (int vv = 0; vv < F; ++vv) {
+            const int x2 = xx + vv - pad;
+            if (y >= 0 && y < S && x2 >= 0 && x2 < S)
+              v[(c * F + u) * F + vv] = img[((size_t)c * S + y) * S + x2];
+          }
+        }
       }
     }
-    reinterpret_cast<uint4 *>(xcol)[t] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
-                                                    pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    uint4 *o = reinterpret_cast<uint4 *>(xcol) + (size_t)t * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      o[q] = make_uint4(pack_bf16x2(v[8 * q], v[8 * q + 1]), pack_bf16x2(v[8 * q + 2], v[8 * q + 3]),
+                        pack_bf16x2(v[8 * q + 4], v[8 * q + 5]), pack_bf16x2(v[8 * q + 6], v[8 * q + 7]));
   }
 }
 // Wcol[m][k] = W[m][c][f-1-u][f-1-v] (k as above), zero padded to 64
@@ -752,10 +762,12 @@ extern "C" int tn_im2col_bf16(const float *x, void *xcol, int B, int C, int S, i
                               void *stream) {
   TN_REQUIRE(x && xcol && B > 0 && C > 0 && S > 0 && f > 0, TN_ERR_ARG, "tn_im2col_bf16: bad argument");
   TN_REQUIRE(C * f * f <= 64, TN_ERR_UNSUPPORTED, "tn_im2col_bf16: C*f*f = %d exceeds 64", C * f * f);
-  const int64_t total8 = (int64_t)B * S * S * 8;
-  TN_REQUIRE(total8 < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_im2col_bf16: tensor too large");
-  im2col_bf16_kernel<<<blocks_for(total8), 256, 0, (cudaStream_t)stream>>>(
-      x, (__nv_bfloat16 *)xcol, (uint32_t)total8, C, S, f, pad_lo, FastDiv32(S));
+  const int64_t npix = (int64_t)B * S * S;
+  TN_REQUIRE(npix * 64 < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_im2col_bf16: tensor too large");
+  TN_REQUIRE(f == 3 && C <= 7, TN_ERR_UNSUPPORTED,
+             "tn_im2col_bf16: built for 3x3 filters on <= 7 channels (got f=%d C=%d)", f, C);
+  im2col_bf16_kernel<3><<<blocks_for(npix), 256, 0, (cudaStream_t)stream>>>(
+      x, (__nv_bfloat16 *)xcol, (uint32_t)npix, C, S, f, pad_lo, FastDiv32(S));
   TN_LAUNCH_CHECK("tn_im2col_bf16");
   return TN_OK;
 }

@@ -310,7 +310,8 @@ class NeuralNet():
         C_, S, M, f, O = lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.out_sz
         if _C.lib.tn_conv2d_tc_supported(C_, S, M, f, O):
             return 'tc'
-        if not self.need_below[li] and C_ * f * f <= 64 and _C.lib.tn_conv2d_tc_supported(64, S, M, 1, O):
+        if (not self.need_below[li] and f == 3 and C_ <= 7 and
+                _C.lib.tn_conv2d_tc_supported(64, S, M, 1, O)):
             return 'im2col'
         return None
 
