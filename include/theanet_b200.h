@@ -87,7 +87,8 @@ typedef struct tn_elastic_prm {
 /* noise[2*h*h] ~ N(0,1) float32, Box-Muller on the (seed, step) Philox stream (inlayers.py:94) */
 int tn_elastic_noise(float *noise, int h, uint64_t seed, const int32_t *ctl, void *stream);
 /* The per-minibatch sampling grid (inlayers.py:77-122).  u_inj: 8 injected uniforms or NULL (then
- * drawn from the (seed, step) stream).  filt: the (2*sigma+1)^2 float32 table (inlayers.py:87-91).
+ * drawn from the (seed, step) stream).  noise: the N(0,1) field, or NULL to draw it in-kernel
+ * from the same stream tn_elastic_noise uses.  filt: the (2*sigma+1)^2 table (inlayers.py:87-91).
  * Outputs: target[2*h*h] float64 before clipping (debugout, may be NULL), tyx[2*h*h] float64
  * clipped coordinates (may be NULL), gidx[h*h] int32 gather base (row*h+col), gfrac[2*h*h]
  * float32 (fy, fx) -- written only when !nearest. */
@@ -243,9 +244,11 @@ int tn_softmax_head_fwd_bwd(const float *h, const float *W, const float *bias, c
                             void *stream);
 size_t tn_softmax_head_workspace_bytes(int B, int n_in, int n_out);
 /* dW = h^T.g, db = column sums of g.  `workspace` must be zero-filled ONCE by the caller before
- * the first call (it holds the completion tickets, which every launch leaves at zero). */
+ * the first call (it holds the completion tickets, which every launch leaves at zero).  If rowloss
+ * != NULL the launch also writes nll_sum[0] = sum_b rowloss[b] (what tn_reduce_rowloss computes). */
 int tn_softmax_head_bwd_weights(const float *h, const float *g, float *dW, float *db,
-                                void *workspace, int B, int n_in, int n_out, void *stream);
+                                void *workspace, int B, int n_in, int n_out, const float *rowloss,
+                                float *nll_sum, void *stream);
 
 /* ---- Layer.get_updates / get_wtcost (theanet/layer/layer.py:70-117) ------------------------- */
 typedef struct tn_param_seg {
@@ -265,7 +268,9 @@ size_t tn_update_workspace_bytes(int nseg, int64_t total);
 /* One step for all tensors: g' = g*grad_scale + L1*sgn(theta) + 2*L2*theta;
  * v' = m*v + (1-m)*g'; theta' = theta - rate*lr*v (OLD v); maxnorm on theta'.
  * cost_out[0] = (sum(rowloss[0..n_rowloss)) or nll_sum[0]) * nll_scale + L1/L2 weight cost of the
- * PRE-update theta.  segs_host is copied into the launch (<= 64 segments). lr comes from ctl. */
+ * PRE-update theta.  segs_host is copied into the launch (<= 64 segments). lr comes from ctl.
+ * `workspace` (tn_update_workspace_bytes) must be zero-filled ONCE by the caller before the first
+ * call: its tail is the completion ticket of the cost reduction, left at zero by every launch. */
 int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
                                    const tn_param_seg *segs_host, int nseg, int64_t total,
                                    const int32_t *ctl, float grad_scale, const float *nll_sum,

@@ -489,9 +489,11 @@ def test_softmax_head_fused(C, B, n_in, n_out, pdrop):
     res = []
     for _ in range(2):
         dW, db = torch.zeros_like(Wd), torch.zeros_like(bd)
+        nll = torch.zeros(1, device='cuda')
         C.call('tn_softmax_head_bwd_weights', C.ptr(hd), C.ptr(gd), C.ptr(dW), C.ptr(db), C.ptr(ws),
-               B, n_in, n_out, None)
+               B, n_in, n_out, C.ptr(rl), C.ptr(nll), None)
         sync()
+        assert abs(float(nll) - float(rl.sum())) <= 1e-5 * abs(float(rl.sum()))
         res.append((dW.cpu().numpy(), db.cpu().numpy()))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     g32 = g.astype(np.float32).astype(np.float64)

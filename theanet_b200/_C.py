@@ -81,7 +81,7 @@ SIGNATURES = {
     'tn_softmax_head_fwd_bwd': (_I, [_P] * 6 + [_I, _I, _I, _F] + [_P] * 4 + [_I, _I, _I, _D, _U64,
                                                                             _P, _P]),
     'tn_softmax_head_workspace_bytes': (C.c_size_t, [_I, _I, _I]),
-    'tn_softmax_head_bwd_weights': (_I, [_P] * 5 + [_I, _I, _I, _P]),
+    'tn_softmax_head_bwd_weights': (_I, [_P] * 5 + [_I, _I, _I, _P, _P, _P]),
     'tn_softmax_test_stats': (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
     'tn_update_workspace_bytes': (C.c_size_t, [_I, _I64]),
     'tn_sgd_momentum_maxnorm_update': (_I, [_P, _P, _P, C.POINTER(ParamSeg), _I, _I64, _P, _F,

@@ -12,11 +12,9 @@
 namespace tn {
 
 // ---------------------------------------------------------------------------------------------
-__global__ void elastic_noise_kernel(float *__restrict__ noise, int n, uint64_t seed,
-                                     const int32_t *__restrict__ ctl) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // Philox block index: 4 words -> 4 normals
-  if (4 * t >= n) return;
-  const Philox4 r = philox_block(seed, TN_RNG_NOISE, (uint32_t)ctl[TN_CTL_STEP], 0u, (uint32_t)t);
+// the 4 standard normals of Philox block t of the (seed, step) noise stream (Box-Muller in fp64)
+__device__ __forceinline__ void noise_block(uint64_t seed, uint32_t step, int t, float (&z)[4]) {
+  const Philox4 r = philox_block(seed, TN_RNG_NOISE, step, 0u, (uint32_t)t);
   const double k = 1.0 / 4294967296.0;
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
@@ -27,10 +25,20 @@ __global__ void elastic_noise_kernel(float *__restrict__ noise, int n, uint64_t 
     const double ang = 6.283185307179586 * u2;
     double s, c;
     sincos(ang, &s, &c);
-    const int j = 4 * t + 2 * p;
-    if (j < n) noise[j] = (float)(rad * c);
-    if (j + 1 < n) noise[j + 1] = (float)(rad * s);
+    z[2 * p] = (float)(rad * c);
+    z[2 * p + 1] = (float)(rad * s);
   }
+}
+
+__global__ void elastic_noise_kernel(float *__restrict__ noise, int n, uint64_t seed,
+                                     const int32_t *__restrict__ ctl) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;  // Philox block index: 4 words -> 4 normals
+  if (4 * t >= n) return;
+  float z[4];
+  noise_block(seed, (uint32_t)ctl[TN_CTL_STEP], t, z);
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (4 * t + q < n) noise[4 * t + q] = z[q];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -60,8 +68,19 @@ __global__ void elastic_field_kernel(tn_elastic_prm prm, const float *__restrict
 
   if (prm.magnitude != 0.f) {
     for (int i = threadIdx.x; i < k * k; i += blockDim.x) s_filt[i] = filt[i];
-    for (int i = threadIdx.x; i < 2 * hw; i += blockDim.x)
-      s_el[i] = __fmul_rn(prm.magnitude, noise[i]);
+    if (noise) {
+      for (int i = threadIdx.x; i < 2 * hw; i += blockDim.x)
+        s_el[i] = __fmul_rn(prm.magnitude, noise[i]);
+    } else {   // draw the field here (every CTA needs all of it): one launch less per step
+      const uint32_t step = (uint32_t)ctl[TN_CTL_STEP];
+      for (int t = threadIdx.x; 4 * t < 2 * hw; t += blockDim.x) {
+        float z[4];
+        noise_block(seed, step, t, z);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * t + q < 2 * hw) s_el[4 * t + q] = __fmul_rn(prm.magnitude, z[q]);
+      }
+    }
   }
   if (threadIdx.x == 0) {
     float u[8];
@@ -259,8 +278,8 @@ extern "C" int tn_elastic_field(const tn_elastic_prm *prm, const float *noise, c
   TN_REQUIRE(prm->h > 0 && prm->sigma >= 0, TN_ERR_SHAPE, "tn_elastic_field: bad h/sigma");
   TN_REQUIRE(u_inj || ctl, TN_ERR_ARG, "tn_elastic_field: need ctl or injected uniforms");
   TN_REQUIRE(prm->nearest || gfrac, TN_ERR_ARG, "tn_elastic_field: bilinear needs gfrac");
-  TN_REQUIRE(prm->magnitude == 0.f || (noise && filt), TN_ERR_ARG,
-             "tn_elastic_field: magnitude != 0 needs noise and filter table");
+  TN_REQUIRE(prm->magnitude == 0.f || (filt && (noise || ctl)), TN_ERR_ARG,
+             "tn_elastic_field: magnitude != 0 needs the filter table and noise (or ctl to draw it)");
   const int k = 2 * prm->sigma + 1;
   const int hw = prm->h * prm->h;
   const size_t smem = prm->magnitude != 0.f ? (size_t)(k * k + 2 * hw) * sizeof(float) : 0;

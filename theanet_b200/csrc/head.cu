@@ -175,7 +175,8 @@ constexpr int kHeadChunk = 128;  // batch rows per CTA
 template <int NP>
 __global__ void __launch_bounds__(256)
 head_dw_kernel(const float *__restrict__ h, const float *__restrict__ g, float *__restrict__ dW,
-               float *__restrict__ db, float *ws_f, int B, int n_in, int n_out) {
+               float *__restrict__ db, float *ws_f, int B, int n_in, int n_out,
+               const float *__restrict__ rowloss, float *__restrict__ nll_sum) {
   __shared__ float red[8][NP][33];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -242,6 +243,19 @@ head_dw_kernel(const float *__restrict__ h, const float *__restrict__ g, float *
     float s = 0.f;
     for (int c = 0; c < nchunks; ++c) s += __ldcg(part_b + (size_t)c * n_out + threadIdx.x);
     db[threadIdx.x] = s;
+  }
+  if (tile == 0 && rowloss) {   // nll_sum = sum_b rowloss[b]: strided partials, fixed-order tree
+    __syncthreads();
+    float *r1 = &red[0][0][0];
+    float s = 0.f;
+    for (int b = threadIdx.x; b < B; b += 256) s += rowloss[b];
+    r1[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (threadIdx.x < o) r1[threadIdx.x] += r1[threadIdx.x + o];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) nll_sum[0] = r1[0];
   }
 }
 
@@ -318,18 +332,19 @@ extern "C" size_t tn_softmax_head_workspace_bytes(int B, int n_in, int n_out) {
 
 extern "C" int tn_softmax_head_bwd_weights(const float *h, const float *g, float *dW, float *db,
                                            void *workspace, int B, int n_in, int n_out,
-                                           void *stream) {
+                                           const float *rowloss, float *nll_sum, void *stream) {
   const char *who = "tn_softmax_head_bwd_weights";
-  TN_REQUIRE(h && g && dW && db && workspace, TN_ERR_ARG, "%s: null argument", who);
+  TN_REQUIRE(h && g && dW && db && workspace && (!rowloss || nll_sum), TN_ERR_ARG,
+             "%s: null argument", who);
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0 && n_out <= 32, TN_ERR_UNSUPPORTED,
              "%s: needs n_out <= 32 (got %d)", who, n_out);
   dim3 grid(ceil_div(n_in, 32), ceil_div(B, kHeadChunk));
   cudaStream_t st = (cudaStream_t)stream;
   float *ws = (float *)workspace;
-  if (n_out <= 8) head_dw_kernel<8><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out);
-  else if (n_out <= 12) head_dw_kernel<12><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out);
-  else if (n_out <= 16) head_dw_kernel<16><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out);
-  else head_dw_kernel<32><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out);
+  if (n_out <= 8) head_dw_kernel<8><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  else if (n_out <= 12) head_dw_kernel<12><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  else if (n_out <= 16) head_dw_kernel<16><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  else head_dw_kernel<32><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
 }

@@ -23,8 +23,11 @@ struct SegTable {
 __global__ void __launch_bounds__(kUpdThreads)
 sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float *__restrict__ grad,
                 const __grid_constant__ SegTable tab, const int32_t *__restrict__ ctl,
-                float grad_scale, float *__restrict__ wt_partial) {
+                float grad_scale, float *__restrict__ wt_partial, int *ticket,
+                const float *__restrict__ nll_sum, float nll_scale, float *__restrict__ cost_out) {
   __shared__ float red[kUpdThreads / 32];
+  __shared__ float red2[kUpdThreads];
+  __shared__ int s_last;
   int s = 0;
   while (s + 1 < tab.nseg && (int)blockIdx.x >= tab.first_block[s + 1]) ++s;
   const tn_param_seg &sg = tab.seg[s];
@@ -69,6 +72,28 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
     for (int w = 0; w < kUpdThreads / 32; ++w) t += red[w];
     wt_partial[blockIdx.x] = t;
   }
+  if (!cost_out) return;
+  // the last CTA to finish (ticket) adds the per-CTA weight-cost partials in a fixed order:
+  // cost = nll * nll_scale + L1/L2 cost of the PRE-update theta  (no second launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(ticket, 1);
+    s_last = t == (int)gridDim.x - 1;
+    if (s_last) *ticket = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float csum = 0.f;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += kUpdThreads) csum += __ldcg(wt_partial + i);
+  red2[threadIdx.x] = csum;
+  __syncthreads();
+  for (int o = kUpdThreads / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red2[threadIdx.x] += red2[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cost_out[0] = (nll_sum ? nll_sum[0] * nll_scale : 0.f) + red2[0];
 }
 
 __device__ __forceinline__ float maxnorm_scale(float sumsq, float maxnorm) {
@@ -150,8 +175,8 @@ static int64_t update_blocks(const tn_param_seg *segs, int nseg, int *first_bloc
 using namespace tn;
 
 extern "C" size_t tn_update_workspace_bytes(int nseg, int64_t total) {
-  // one float per CTA of the step kernel; bounded by total/1024 + nseg
-  return (size_t)(total / kUpdPerBlock + nseg + 1) * sizeof(float);
+  // one float per CTA of the step kernel (bounded by total/1024 + nseg) + the completion ticket
+  return (size_t)(total / kUpdPerBlock + nseg + 1) * sizeof(float) + 16;
 }
 
 extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
@@ -175,8 +200,10 @@ extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const fl
   const int64_t nb = update_blocks(segs, nseg, tab.first_block);
   cudaStream_t st = (cudaStream_t)stream;
   float *wt_partial = (float *)workspace;
+  int *ticket = reinterpret_cast<int *>(wt_partial + (total / kUpdPerBlock + nseg + 1));
   sgd_step_kernel<<<(unsigned)nb, kUpdThreads, 0, st>>>(theta, vel, grad, tab, ctl, grad_scale,
-                                                        wt_partial);
+                                                        wt_partial, ticket, nll_sum, nll_scale,
+                                                        cost_out);
   TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(step)");
   for (int s = 0; s < nseg; ++s) {
     const tn_param_seg &sg = segs[s];
@@ -189,10 +216,6 @@ extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const fl
                                                                 sg.cols, sg.maxnorm);
     }
     TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(maxnorm)");
-  }
-  if (cost_out) {
-    finish_cost_kernel<<<1, 256, 0, st>>>(wt_partial, (int)nb, nll_sum, nll_scale, cost_out);
-    TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(cost)");
   }
   return TN_OK;
 }

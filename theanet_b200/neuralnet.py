@@ -291,7 +291,7 @@ class NeuralNet():
             nb = _C.lib.tn_softmax_head_workspace_bytes(B, last.n_in, last.n_out)
             self.ws_head = torch.zeros((nb + 3) // 4, dtype=f32, device=dev)   # tickets start at 0
         nb = _C.lib.tn_update_workspace_bytes(max(1, self.n_segs), total)
-        self.ws_update = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
+        self.ws_update = torch.zeros((nb + 3) // 4, dtype=f32, device=dev)    # ticket starts at 0
         self._graphs = {}
         self.launches = {}          # 'train' / 'test' -> kernels of this library per step
         if self.dist.world > 1:     # replicas must start identical (rank 0 wins)
@@ -413,10 +413,7 @@ class NeuralNet():
                 if train and isinstance(lyr, ElasticLayer) and not lyr.identity:
                     seed = lyr.seed
                     if lyr.has_grid:
-                        noise = self._inj(0, 'noise')
-                        if lyr.magnitude and noise is None:
-                            _C.call('tn_elastic_noise', _C.ptr(self.el_noise), h, seed, ctl, st)
-                            noise = _C.ptr(self.el_noise)
+                        noise = self._inj(0, 'noise')     # None: drawn inside tn_elastic_field
                         dbg = self.debug_elastic
                         _C.call('tn_elastic_field', ctypes.byref(self.el_prm), noise,
                                 self._inj(0, 'u'), _C.ptr(self.el_filt), seed, ctl,
@@ -546,7 +543,7 @@ class NeuralNet():
                 with self._wgrad_stream() as sw:
                     _C.call('tn_softmax_head_bwd_weights', _C.ptr(x), _C.ptr(g),
                             _C.ptr(lyr.w.grad), _C.ptr(lyr.b.grad), _C.ptr(self.ws_head), B,
-                            lyr.n_in, lyr.n_out, sw)
+                            lyr.n_in, lyr.n_out, _C.ptr(self.rowloss), _C.ptr(self.nll_sum), sw)
             elif isinstance(lyr, HiddenLayer):
                 if self.trainable[li]:
                     with self._wgrad_stream() as sw:
@@ -681,7 +678,8 @@ class NeuralNet():
                     _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
         self._backward()
         self._join_wgrad()
-        _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
+        if not self.head:                      # the fused head already reduced the row losses
+            _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
         if self.dist.world > 1 and not self.nccl_in_graph:
             return                                   # the caller reduces, then _update_launches
         self.dist.all_reduce_sum(self.grad)          # the one collective of the step
