@@ -380,7 +380,10 @@ def run_ours(args):
                    "parallelism": "dp{}".format(world),
                    "l2": "corpus of {} minibatches ({} MB per GPU) cycled, larger than the 126 MB "
                          "L2; no explicit flush".format(nb, nb * PER_GPU_BATCH * IMG * IMG * 4 // 10 ** 6),
-                   "cuda_graph": bool(net.use_graph)},
+                   "cuda_graph": bool(net.use_graph),
+                   "collective": ("none" if world == 1 else
+                                  "fused into the update kernel over CUDA-IPC peer memory (NVLink)"
+                                  if net.dp_fused else "NCCL all-reduce of the flat gradient buffer")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roof, "cpu_baseline": cpu,
         "step_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes,

@@ -276,6 +276,23 @@ int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
                                    const int32_t *ctl, float grad_scale, const float *nll_sum,
                                    float nll_scale, float *cost_out, void *workspace,
                                    void *stream);
+/* Data parallel, fused: the same update with the gradient all-reduce folded in.  peer_grads[r] /
+ * peer_flags[r] (host arrays of `world` device pointers) are rank r's flat gradient buffer
+ * (total + 4 floats; [total] is its NLL partial sum) and flag array (int[8], zero-filled once),
+ * mapped into this process with tn_ipc_open_handle (entry [rank] is the local buffer).  The kernel
+ * signals and waits for all ranks, sums the buffers in rank order while it updates, and needs the
+ * caller to alternate between two gradient buffers from step to step (see update.cu). */
+int tn_allreduce_sgd_update(float *theta, float *vel, const float *const *peer_grads,
+                            int *const *peer_flags, int world, int rank,
+                            const tn_param_seg *segs_host, int nseg, int64_t total,
+                            const int32_t *ctl, float grad_scale, float nll_scale, float *cost_out,
+                            void *workspace, void *stream);
+/* peer-mappable device memory (cudaMalloc, zero-filled) and CUDA-IPC handles (64 bytes) */
+int tn_peer_alloc(size_t bytes, void **ptr);
+int tn_peer_free(void *ptr);
+int tn_ipc_get_handle(void *ptr, void *handle_out);
+int tn_ipc_open_handle(const void *handle, void **ptr);
+int tn_ipc_close_handle(void *ptr);
 /* nll_sum[0] = sum_b rowloss[b] (fixed order, deterministic) */
 int tn_reduce_rowloss(const float *rowloss, int B, float *nll_sum, void *stream);
 

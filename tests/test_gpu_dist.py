@@ -10,13 +10,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('graph', [0, 1])
-def test_two_gpu_data_parallel_matches_oracle(graph):
+@pytest.mark.parametrize('graph,fused', [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_two_gpu_data_parallel_matches_oracle(graph, fused):
+    """fused = 1: gradient all-reduce folded into the optimiser kernel over CUDA-IPC peer memory."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-           '--master-addr', '127.0.0.1', '--master-port', str(29600 + graph),
+           '--master-addr', '127.0.0.1', '--master-port', str(29600 + graph + 2 * fused),
            os.path.join(ROOT, 'tools', 'dp_check.py'), '--graph', str(graph)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT)
+    env = dict(os.environ, TN_DP_FUSED=str(fused))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=180, cwd=ROOT, env=env)
     assert 'DP_CHECK_OK world=2' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

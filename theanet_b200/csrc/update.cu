@@ -14,6 +14,31 @@ constexpr int kMaxSegs = 64;
 constexpr int kUpdThreads = 256;
 constexpr int kUpdPerBlock = kUpdThreads * 4;
 
+// Fused data-parallel step: instead of an NCCL all-reduce followed by the update,
+// every rank reads the gradient buffers of ALL ranks directly over NVLink (CUDA-IPC mapped peer
+// memory) and adds them in rank order -- the same order everywhere, so the replicas stay bit
+// identical -- inside the optimiser kernel itself.  Handshake: each rank stores a step token into
+// every peer's flag array when its own gradients are complete (it is the first thing this kernel
+// does, after all backward kernels in stream order) and spins until all tokens have arrived.
+// Gradient buffers are double-buffered by step parity, which makes the "peers are done reading"
+// direction implicit: a buffer is rewritten two steps later, after its owner has passed the next
+// step's handshake, which every reader only enters once it has finished this step's reads.
+constexpr int kMaxPeers = 8;
+struct PeerArgs {
+  const float *grad[kMaxPeers];   // grad[r]: rank r's gradient buffer of this parity (r == rank: local)
+  int *flags[kMaxPeers];          // flags[r]: rank r's flag array (int[kMaxPeers]); [rank] is local
+  int world, rank;
+};
+
+__device__ __forceinline__ void st_release_sys(int *p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 struct SegTable {
   tn_param_seg seg[kMaxSegs];
   int first_block[kMaxSegs + 1];
@@ -24,10 +49,27 @@ __global__ void __launch_bounds__(kUpdThreads)
 sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float *__restrict__ grad,
                 const __grid_constant__ SegTable tab, const int32_t *__restrict__ ctl,
                 float grad_scale, float *__restrict__ wt_partial, int *ticket,
-                const float *__restrict__ nll_sum, float nll_scale, float *__restrict__ cost_out) {
+                const float *__restrict__ nll_sum, float nll_scale, float *__restrict__ cost_out,
+                const __grid_constant__ PeerArgs peers, int64_t nll_slot) {
   __shared__ float red[kUpdThreads / 32];
   __shared__ float red2[kUpdThreads];
   __shared__ int s_last;
+  const int W = peers.world;
+  if (W > 1) {
+    const int token = ctl[TN_CTL_STEP] + 1;
+    if (blockIdx.x == 0 && threadIdx.x < W) {
+      __threadfence_system();
+      st_release_sys(peers.flags[threadIdx.x] + peers.rank, token);   // "my gradients are complete"
+    }
+    if (threadIdx.x < W) {
+      const int *f = peers.flags[peers.rank] + threadIdx.x;
+      const long long t0 = clock64();
+      while (ld_acquire_sys(f) - token < 0) {
+        if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died; fail loudly
+      }
+    }
+    __syncthreads();
+  }
   int s = 0;
   while (s + 1 < tab.nseg && (int)blockIdx.x >= tab.first_block[s + 1]) ++s;
   const tn_param_seg &sg = tab.seg[s];
@@ -47,7 +89,14 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
       if (sg.l1 != 0.f) wsum = fmaf(sg.l1, fabsf(th), wsum);
       if (sg.l2 != 0.f) wsum = fmaf(sg.l2, th * th, wsum);
       if (sg.rate != 0.f) {
-        float g = grad_scale == 1.f ? grad[i] : __fmul_rn(grad[i], grad_scale);
+        float gi;
+        if (W > 1) {   // sum over ranks in rank order, L1 bypassed (peer data changes every step)
+          gi = __ldcg(peers.grad[0] + i);
+          for (int r = 1; r < W; ++r) gi = __fadd_rn(gi, __ldcg(peers.grad[r] + i));
+        } else {
+          gi = grad[i];
+        }
+        float g = grad_scale == 1.f ? gi : __fmul_rn(gi, grad_scale);
         if (sg.l1 != 0.f) {
           const float sgn = th > 0.f ? 1.f : (th < 0.f ? -1.f : 0.f);
           g = __fadd_rn(g, __fmul_rn(sg.l1, sgn));
@@ -93,7 +142,15 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
     if (threadIdx.x < o) red2[threadIdx.x] += red2[threadIdx.x + o];
     __syncthreads();
   }
-  if (threadIdx.x == 0) cost_out[0] = (nll_sum ? nll_sum[0] * nll_scale : 0.f) + red2[0];
+  if (threadIdx.x == 0) {
+    float nll = 0.f;
+    if (W > 1) {
+      for (int r = 0; r < W; ++r) nll = __fadd_rn(nll, __ldcg(peers.grad[r] + nll_slot));
+    } else if (nll_sum) {
+      nll = nll_sum[0];
+    }
+    cost_out[0] = nll * nll_scale + red2[0];
+  }
 }
 
 __device__ __forceinline__ float maxnorm_scale(float sumsq, float maxnorm) {
@@ -179,11 +236,10 @@ extern "C" size_t tn_update_workspace_bytes(int nseg, int64_t total) {
   return (size_t)(total / kUpdPerBlock + nseg + 1) * sizeof(float) + 16;
 }
 
-extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
-                                              const tn_param_seg *segs, int nseg, int64_t total,
-                                              const int32_t *ctl, float grad_scale,
-                                              const float *nll_sum, float nll_scale,
-                                              float *cost_out, void *workspace, void *stream) {
+static int update_impl(float *theta, float *vel, const float *grad, const tn_param_seg *segs,
+                       int nseg, int64_t total, const int32_t *ctl, float grad_scale,
+                       const float *nll_sum, float nll_scale, float *cost_out, void *workspace,
+                       const PeerArgs &peers, void *stream) {
   TN_REQUIRE(theta && vel && grad && segs && ctl && workspace, TN_ERR_ARG,
              "tn_sgd_momentum_maxnorm_update: null argument");
   TN_REQUIRE(nseg > 0 && nseg <= kMaxSegs, TN_ERR_UNSUPPORTED,
@@ -203,7 +259,7 @@ extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const fl
   int *ticket = reinterpret_cast<int *>(wt_partial + (total / kUpdPerBlock + nseg + 1));
   sgd_step_kernel<<<(unsigned)nb, kUpdThreads, 0, st>>>(theta, vel, grad, tab, ctl, grad_scale,
                                                         wt_partial, ticket, nll_sum, nll_scale,
-                                                        cost_out);
+                                                        cost_out, peers, total);
   TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(step)");
   for (int s = 0; s < nseg; ++s) {
     const tn_param_seg &sg = segs[s];
@@ -218,4 +274,35 @@ extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const fl
     TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(maxnorm)");
   }
   return TN_OK;
+}
+
+extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
+                                              const tn_param_seg *segs, int nseg, int64_t total,
+                                              const int32_t *ctl, float grad_scale,
+                                              const float *nll_sum, float nll_scale,
+                                              float *cost_out, void *workspace, void *stream) {
+  PeerArgs peers{};
+  peers.world = 1;
+  return update_impl(theta, vel, grad, segs, nseg, total, ctl, grad_scale, nll_sum, nll_scale,
+                     cost_out, workspace, peers, stream);
+}
+
+extern "C" int tn_allreduce_sgd_update(float *theta, float *vel, const float *const *peer_grads,
+                                       int *const *peer_flags, int world, int rank,
+                                       const tn_param_seg *segs, int nseg, int64_t total,
+                                       const int32_t *ctl, float grad_scale, float nll_scale,
+                                       float *cost_out, void *workspace, void *stream) {
+  TN_REQUIRE(peer_grads && peer_flags && world >= 1 && world <= kMaxPeers && rank >= 0 &&
+                 rank < world,
+             TN_ERR_ARG, "tn_allreduce_sgd_update: bad peer arguments (world %d, rank %d)", world, rank);
+  PeerArgs peers{};
+  peers.world = world;
+  peers.rank = rank;
+  for (int r = 0; r < world; ++r) {
+    TN_REQUIRE(peer_grads[r] && peer_flags[r], TN_ERR_ARG, "tn_allreduce_sgd_update: null peer %d", r);
+    peers.grad[r] = peer_grads[r];
+    peers.flags[r] = peer_flags[r];
+  }
+  return update_impl(theta, vel, peer_grads[rank], segs, nseg, total, ctl, grad_scale, nullptr,
+                     nll_scale, cost_out, workspace, peers, stream);
 }

@@ -187,15 +187,26 @@ class NeuralNet():
         self.theta = torch.zeros(total, dtype=f32, device=dev)
         self.vel = torch.zeros(total, dtype=f32, device=dev)
         # gradient buffer + 4 trailing floats: [nll partial sum, pad]; one all-reduce covers both
-        self.grad = torch.zeros(total + 4, dtype=f32, device=dev)
-        self.nll_sum = self.grad[total:total + 1]
+        # data parallel: either one NCCL all-reduce of `grad` per step, or (TN_DP_FUSED=1) the
+        # all-reduce folded into the optimiser kernel over CUDA-IPC mapped peer buffers, with the
+        # gradient buffer double-buffered by step parity (update.cu)
+        self.dp_fused = self.dist.world > 1 and os.environ.get('TN_DP_FUSED', '0') == '1'
+        if self.dp_fused:
+            from .dist import PeerBuffers
+            self.peers = PeerBuffers(self.dist, total + 4, dev)
+            self.grads2 = self.peers.grad
+        else:
+            self.grads2 = [torch.zeros(total + 4, dtype=f32, device=dev)]
         self.params = params
         self.param_offset = dict()
+        self._grad_views = []
+        for gbuf in self.grads2:
+            self._grad_views.append([gbuf[o:o + p.size].view(p.shape) for p, o in zip(params, offs)])
         for p, o in zip(params, offs):
             shp = p.shape
-            p.bind(self.theta[o:o + p.size].view(shp), self.vel[o:o + p.size].view(shp),
-                   self.grad[o:o + p.size].view(shp))
+            p.bind(self.theta[o:o + p.size].view(shp), self.vel[o:o + p.size].view(shp), None)
             self.param_offset[id(p)] = o
+        self._bind_grads(0)
         # optimiser segment table (theanet/layer/layer.py:70-107)
         segs = []
         for lyr in self.tr_layers:
@@ -296,6 +307,15 @@ class NeuralNet():
         self.launches = {}          # 'train' / 'test' -> kernels of this library per step
         if self.dist.world > 1:     # replicas must start identical (rank 0 wins)
             torch.distributed.broadcast(self.theta, src=0, group=self.dist.group)
+
+    def _bind_grads(self, parity):
+        """Point every parameter's .grad (and the NLL slot) at the gradient buffer of this parity."""
+        k = parity % len(self.grads2)
+        self.grad = self.grads2[k]
+        self.nll_sum = self.grad[self.n_flat:self.n_flat + 1]
+        for p, v in zip(self.params, self._grad_views[k]):
+            p.grad = v
+        self._grad_parity = k
 
     # ------------------------------------------------------------------------------------------
     # mixed-precision conv stack (training_params['CONV_DTYPE'] = 'bfloat16'; config C4)
@@ -680,6 +700,12 @@ class NeuralNet():
         self._join_wgrad()
         if not self.head:                      # the fused head already reduced the row losses
             _C.call('tn_reduce_rowloss', _C.ptr(self.rowloss), B, _C.ptr(self.nll_sum), st)
+        if self.dp_fused:                            # all-reduce inside the optimiser kernel
+            _C.call('tn_allreduce_sgd_update', _C.ptr(self.theta), _C.ptr(self.vel),
+                    self.peers.grad_ptrs[self._grad_parity], self.peers.flag_ptrs, self.dist.world,
+                    self.dist.rank, self.segs, self.n_segs, self.n_flat, _C.ptr(self.ctl), 1.0,
+                    1.0 / self.batch_sz, _C.ptr(self.cost), _C.ptr(self.ws_update), st)
+            return
         if self.dist.world > 1 and not self.nccl_in_graph:
             return                                   # the caller reduces, then _update_launches
         self.dist.all_reduce_sum(self.grad)          # the one collective of the step
@@ -695,7 +721,12 @@ class NeuralNet():
         """One training step.  Single GPU: one CUDA graph.  Data parallel: graph (forward +
         backward) -> NCCL all-reduce of the flat gradient buffer -> graph (update); set
         TN_GRAPH_NCCL=1 to capture the collective inside a single graph instead."""
-        if self.dist.world > 1 and not self.nccl_in_graph:
+        if self.dp_fused:
+            parity = self.step_count & 1              # graphs bake pointers: one per parity
+            self._bind_grads(parity)
+            self._run(key + ('p%d' % parity,), self._train_launches, (corpus, idx, labels),
+                      restore=(self.theta, self.vel))
+        elif self.dist.world > 1 and not self.nccl_in_graph:
             self._run(('train_pre',) + key[1:], self._train_launches, (corpus, idx, labels))
             self.dist.all_reduce_sum(self.grad)
             self._run(('update',), self._update_launches, (), restore=(self.theta, self.vel))
