@@ -81,6 +81,25 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   const float l2x2 = 2.f * sg.l2;
   const bool clip1d = sg.ndim == 1 && sg.maxnorm != 0.f;
   float wsum = 0.f;
+  // data parallel: fetch this thread's 4 elements from every rank up front (4 x W independent
+  // NVLink loads in flight, L1 bypassed: peer data changes every step), then add in rank order
+  float gsum[4] = {0.f, 0.f, 0.f, 0.f};
+  if (W > 1) {
+    float gp[4][kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int64_t i = base + q * kUpdThreads + threadIdx.x;
+#pragma unroll
+      for (int r = 0; r < kMaxPeers; ++r) gp[q][r] = (r < W && i < end) ? __ldcg(peers.grad[r] + i) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      gsum[q] = gp[q][0];
+#pragma unroll
+      for (int r = 1; r < kMaxPeers; ++r)
+        if (r < W) gsum[q] = __fadd_rn(gsum[q], gp[q][r]);
+    }
+  }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int64_t i = base + q * kUpdThreads + threadIdx.x;
@@ -89,13 +108,7 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
       if (sg.l1 != 0.f) wsum = fmaf(sg.l1, fabsf(th), wsum);
       if (sg.l2 != 0.f) wsum = fmaf(sg.l2, th * th, wsum);
       if (sg.rate != 0.f) {
-        float gi;
-        if (W > 1) {   // sum over ranks in rank order, L1 bypassed (peer data changes every step)
-          gi = __ldcg(peers.grad[0] + i);
-          for (int r = 1; r < W; ++r) gi = __fadd_rn(gi, __ldcg(peers.grad[r] + i));
-        } else {
-          gi = grad[i];
-        }
+        const float gi = W > 1 ? gsum[q] : grad[i];
         float g = grad_scale == 1.f ? gi : __fmul_rn(gi, grad_scale);
         if (sg.l1 != 0.f) {
           const float sgn = th > 0.f ? 1.f : (th < 0.f ? -1.f : 0.f);
