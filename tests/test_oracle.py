@@ -302,3 +302,39 @@ def test_test_twin_scales_dropout():
     W2, b2 = net.spec[2]['params']
     assert np.allclose(logprob, O.log_softmax(h @ W2 + b2))
     assert np.array_equal(preds, logprob.argmax(1))
+
+
+def test_bf16_rounding_matches_torch_and_eligibility():
+    """The oracle's bf16 emulation (NOT reference behaviour: theanet_b200's optional mixed-precision
+    conv stack, config C4) rounds exactly like torch / the GPU (round to nearest even)."""
+    import torch
+    rng = np.random.default_rng(3)
+    x = np.concatenate([(rng.standard_normal(100000) * 10.0 ** rng.integers(-6, 6, 100000)).astype(np.float32),
+                        np.array([1.00390625, 1.01171875, -1.00390625, 0., 65504.], np.float32)])
+    want = torch.from_numpy(x).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(O.bf16_round(x), want)
+    assert O.conv_tc_eligible(64, 16, 128, 3, 'same', 'relu05', 16, 2)
+    assert O.conv_tc_eligible(3, 32, 64, 3, 'same', 'relu05', 32, 2, first=True)       # im2col
+    assert not O.conv_tc_eligible(3, 32, 64, 3, 'same', 'relu05', 32, 2, first=False)
+    assert not O.conv_tc_eligible(64, 16, 128, 3, 'valid', 'relu05', 14, 2)
+    assert not O.conv_tc_eligible(64, 16, 128, 3, 'same', 'tanh', 16, 2)
+    assert not O.conv_tc_eligible(64, 28, 128, 3, 'same', 'relu05', 28, 2)              # 28 does not tile
+
+
+def test_bf16_conv_stack_mode_changes_only_eligible_layers():
+    prms = load_prms('mnist.prms')
+    prms['training_params'].update(SEED=5, BATCH_SZ=4, CONV_DTYPE='bfloat16')
+    prms['layers'][0][1]['img_sz'] = 28
+    on = O.OracleNet(prms['layers'], prms['training_params'])
+    assert not any(L['tc'] for L in on.spec)        # 'valid' 4/20-map convs stay float32
+    p2 = ast.literal_eval(open(os.path.join(ROOT, 'params', 'cifar3conv.prms')).read())
+    p2['training_params'].update(SEED=5, BATCH_SZ=2, CONV_DTYPE='bfloat16')
+    p2['layers'][0][1]['img_sz'] = 32
+    on2 = O.OracleNet(p2['layers'], p2['training_params'])
+    assert [L['tc'] for L in on2.spec if L['kind'] == 'ConvLayer'] == [True, True, True]
+    rng = np.random.default_rng(0)
+    x = rng.random((2, 3, 32, 32), dtype=np.float32)
+    cost, lp = on2.train_step(x, np.array([1, 7]), step=0)
+    assert np.isfinite(cost) and lp.shape == (2, 10)
+    a = on2._forward(x, False, 0, 0)[1][1]['a']     # conv 1 activations are bf16 values
+    assert np.array_equal(O.bf16_round(a), a)
