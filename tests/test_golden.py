@@ -1,5 +1,5 @@
-"""Golden vectors (tests/golden/, produced by tools/make_golden.py from the oracle -- the reference
-has no result-pinning tests and cannot run here: "parity unpinned").  CPU: the oracle
+"""Golden vectors produced by tools/make_golden.py from the oracle with the product's Philox streams
+(the vectors recorded from the reference's own code are in tests/test_golden_ref.py).  CPU: the oracle
 still reproduces them.  GPU (-m gpu): the CUDA path reproduces them through the public API."""
 import ast
 import copy

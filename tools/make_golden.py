@@ -1,9 +1,9 @@
 """Generate the golden vectors under tests/golden/ from the CPU oracle.
 
-The reference (rakeshvar/theanet) cannot run here -- Theano is not installable in this image
- -- and its own tests pin no results, so these fixtures are produced
-by the restatement in oracle/ ("parity unpinned").  They freeze the oracle against
-regressions (tests/test_golden.py, CPU) and give the GPU path a fixed target (-m gpu).
+These fixtures use the PRODUCT's Philox random streams, which only the oracle (not the reference)
+can reproduce; the vectors recorded from the reference's own code, with its own draws, are made by
+tests/golden/make_golden_ref.py.  They freeze the oracle against regressions (tests/test_golden.py,
+CPU) and give the GPU path a fixed target for networks with random layers (-m gpu).
 
     python tools/make_golden.py            # rewrites tests/golden/*.npz
 """
