@@ -114,7 +114,6 @@ def cpu_step_time(budget_s, batch, steps=None, warmup=1):
     """images/s of oracle.OracleNet.train_step (numpy + BLAS, all host threads) on `batch`-image
     minibatches of the same workload."""
     from oracle import theanet_oracle as O          # checker / baseline only
-    O.CONV_ACCUM = None        # time float32 BLAS convolutions (floatX), not the tie-stable float64 ones
     p = load_prms(batch)
     on = O.OracleNet(p['layers'], p['training_params'])
     x, y = synth_corpus(batch * 2)

@@ -117,12 +117,14 @@ def _im2col(xp, f, out_sz):
     return np.ascontiguousarray(v).reshape(C * f * f, B * out_sz * out_sz)
 
 
-# Accumulation type of the forward convolution.  float64 (then rounded to the working dtype) makes
-# the result independent of the summation order, so that patches with identical inputs give
-# bit-identical outputs wherever they sit in the image -- BLAS float32 GEMMs do not guarantee that
-# (edge micro-kernels sum in another order), and max-pool ties (A3) then break at random.
-# bench.py's CPU-baseline legs set this to None (= accumulate in the working dtype, as Theano would).
-CONV_ACCUM = np.float64
+# Accumulation type of the forward convolution: None = the working dtype (float32 BLAS GEMM, what
+# Theano's CorrMM does); np.float64 = accumulate in double and round once, which makes the result
+# independent of the summation order.  It matters only for max-pool ties (A3) between sums that
+# are equal mathematically but not operand for operand (binary +-c conv weights over duplicated or
+# flat non-zero pixels): there each float32 implementation -- BLAS, cuDNN-style kernels, ours --
+# breaks or keeps the tie according to its own summation order, and no order is canonical.  Tests
+# therefore use data whose ties are exact in any order (zero background); see DESIGN.md section 2.
+CONV_ACCUM = None
 
 
 def conv_forward(x, W, mode='valid'):

@@ -77,17 +77,19 @@ CASES = {
 
 
 def case_data(name):
-    """Deterministic corpus: images in [0,1] with a flat zero background, so that patches with
-    identical inputs -- exact ties inside pooling windows (A3) and pre-activations exactly equal to
-    the bias, 0 for reluNN (A5) -- occur in the first conv layer.  The foreground is NOT quantised:
-    ties between different sums would depend on the summation order of the convolution, which
-    differs between any two implementations."""
+    """Deterministic corpus: images in [0,1] whose top third is a flat background that reaches the
+    first conv layer as exact zeros, so that exact ties inside pooling windows (A3) and
+    pre-activations exactly equal to the bias -- 0 for reluNN (A5) -- occur and do not depend on
+    the summation order of the convolution (a sum of zeros is exact in any order; a flat non-zero
+    background under the reference's binary +-c conv weights is not, and every float32
+    implementation then breaks those ties its own way).  The foreground is not quantised."""
     c = CASES[name]
     img = c['layers'][0][1]['img_sz']
     n = c['tp']['BATCH_SZ'] * c['batches']
     rs = np.random.RandomState(sum(map(ord, name)))
     x = rs.rand(n, c['channels'], img, img).astype(np.float32)
-    x[:, :, :img // 3, :] = 0
+    # 'mnist' inverts its input (invert_image): paint the background 1 so that it is 0 after it
+    x[:, :, :img // 3, :] = 1 if c['layers'][0][1].get('invert_image', False) else 0
     y = rs.randint(0, c['classes'], n).astype(np.int32)
     return x.astype(np.float32), y
 
