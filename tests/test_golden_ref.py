@@ -131,7 +131,7 @@ TOL_GPU = 1e-3      # BASELINE.json north_star: 1e-3 relative in float32 (observ
 # Momentum buffers of networks whose warp duplicates pixels (nearest-neighbour elastic layer): a
 # float32 kernel may break a max-pool tie that the order-independent reference run keeps (see the
 # fixture above); one such window moves the affected conv-gradient entries by a fraction of a
-# per cent for one step.  Weights, costs and log-probabilities stay within TOL_GPU.
+# per cent for one step.  Filter / dense weights, costs and log-probabilities stay within TOL_GPU.
 TOL_GPU_TIES = 2e-2
 
 
@@ -194,10 +194,13 @@ def test_gpu_training_matches_the_reference_graph(name):
     tol_v = TOL_GPU_TIES if c['layers'][0][1].get('nearest', False) else TOL_GPU
     for li, ww in enumerate(net.get_init_params()['allwts']):
         for j, t in enumerate(ww):
-            assert rel(MR.thin(t), g['w_%d' % k]) < TOL_GPU, 'weights %d' % k
+            # biases start at 0 (relu10/relu05, weights.py:64-65): after a few steps they ARE the
+            # accumulated momentum, so they inherit its tolerance
+            tol_w = tol_v if t.ndim == 1 else TOL_GPU
+            assert rel(MR.thin(t), g['w_%d' % k]) < tol_w, 'weights %d' % k
             assert rel(MR.thin(vel[li][j]), g['v_%d' % k]) < tol_v, 'momentum %d' % k
             got, want = MR.digest(t), g['wd_%d' % k]
-            assert abs(got[1] - want[1]) <= 4 * TOL_GPU * want[1] + 1e-30
+            assert abs(got[1] - want[1]) <= 4 * tol_w * want[1] + 1e-30
             k += 1
     assert k == int(g['n_params'])
     test = net.get_test_model(g['x'], g['y'])
