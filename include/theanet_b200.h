@@ -231,6 +231,31 @@ int tn_softmax_test_stats(const float *z, const int32_t *y, const int32_t *idx,
                           const int32_t *ctl, int B, int n, float *logprob, int64_t *preds,
                           float *stats, void *stream);
 
+/* ---- the other output layers and losses (theanet/layer/outlayers.py:38-64,105-147) -------------
+ * kind says how the scores z = x.w + b become (features, logprob, probs):
+ *   TN_OUT_SOFTMAX  SoftmaxLayer   features = logprob = log softmax(z)                 (:83-102)
+ *   TN_OUT_EXPLOSS  ExpLossLayer   o = z - mean_j z; features = o; logprob = log softmax(o) (:105-126)
+ *   TN_OUT_HINGE    HingeLayer     features = logprob = probs = z                       (:129-147)
+ * loss is the per-row term of the cost (cost = sum_b rowloss[b] / global batch):
+ *   TN_LOSS_NLL -lp[y] (:50-51); TN_LOSS_NLLSQ lp[y]^2 (:41-42); TN_LOSS_NLLTRUNC
+ *   max(0, log_threshold - lp[y]) (:44-48, 'nllNN' -> threshold NN/100); TN_LOSS_EXP exp(-o[y])
+ *   (:38-39); TN_LOSS_HINGE mean_j max(0, z_j + 1 - z_y) over ALL j (:62-64).
+ * SOFTMAX takes NLL / NLLSQ / NLLTRUNC, EXPLOSS takes EXP, HINGE takes HINGE (as in the reference's
+ * constructors); anything else is TN_ERR_UNSUPPORTED.  g = dL/dz * inv_global_batch; logprob may
+ * be NULL. */
+enum { TN_OUT_SOFTMAX = 0, TN_OUT_EXPLOSS = 1, TN_OUT_HINGE = 2 };
+enum { TN_LOSS_NLL = 0, TN_LOSS_NLLSQ = 1, TN_LOSS_NLLTRUNC = 2, TN_LOSS_EXP = 3, TN_LOSS_HINGE = 4 };
+int tn_output_loss_fwd_bwd(const float *z, const int32_t *y, const int32_t *idx,
+                           const int32_t *ctl, int B, int n, int kind, int loss,
+                           float log_threshold, float inv_global_batch, float *features,
+                           float *logprob, float *g, float *rowloss, void *stream);
+/* test twin for any kind (outlayers.py:66-80): preds = argmax of the scores (first maximum),
+ * stats[0] = mean(pred != y), stats[1] = mean(probs[y]) -- probs = the raw scores for HINGE
+ * (:138).  features / logprob / preds may be NULL; stats is float[2 + 2*B]. */
+int tn_output_test_stats(const float *z, const int32_t *y, const int32_t *idx, const int32_t *ctl,
+                         int B, int n, int kind, float *features, float *logprob, int64_t *preds,
+                         float *stats, void *stream);
+
 /* ---- classifier head: HiddenLayer -> SoftmaxLayer with n_in <= 1024, n_out <= 32, fused ---------
  * (hidden.py:30-32 + outlayers.py:50-51,83-102 and their gradients in two launches) */
 int tn_softmax_head_supported(int n_in, int n_out);

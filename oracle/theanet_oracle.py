@@ -383,6 +383,71 @@ class InjectedRandom:
 
 
 # ----------------------------------------------------------------------------------------------
+# Output layers and losses -- theanet/layer/outlayers.py:12-147
+# ----------------------------------------------------------------------------------------------
+OUT_LAYERS = ('SoftmaxLayer', 'ExpLossLayer', 'HingeLayer')
+
+
+def output_views(kind, z):
+    """(features, logprob, probs) of an output layer from its scores z = x.w + b."""
+    if kind == 'SoftmaxLayer':                       # :83-102 (A4: stable log-softmax)
+        lp = log_softmax(z)
+        return lp, lp, np.exp(lp)
+    if kind == 'ExpLossLayer':                       # :105-126: rows centred, then softmax
+        o = z - z.mean(axis=1, keepdims=True, dtype=z.dtype)
+        lp = log_softmax(o)
+        return o, lp, np.exp(lp)
+    if kind == 'HingeLayer':                         # :129-147: logprob = probs = features = z
+        return z, z, z
+    raise NotImplementedError(kind)
+
+
+def loss_threshold(loss):
+    """'nllNN' -> NN/100 clipped to [0,1]; unreadable -> 1.0 = plain NLL (outlayers.py:20-27)."""
+    try:
+        return float(np.clip(int(loss[-2:]) / 100, 0, 1))
+    except ValueError:
+        return 1.0
+
+
+def output_loss(kind, loss, z, logprob, y, Bg):
+    """(cost term, dL/dz) with the mean taken over Bg samples.  maximum(0, a) hands the gradient
+    on where a >= 0 (A5)."""
+    dt = z.dtype
+    one = dt.type(1)
+    B, n = z.shape
+    rows = np.arange(B)
+    onehot = np.zeros_like(z)
+    onehot[rows, y] = one
+    if kind == 'SoftmaxLayer':
+        lpy = logprob[rows, y]
+        p = np.exp(logprob)
+        if loss == 'nll':                                                    # :50-51
+            per, dl = -lpy, -np.ones_like(lpy)
+        elif loss == 'nllsq':                                                # :41-42
+            per, dl = lpy * lpy, dt.type(2) * lpy
+        elif loss.startswith('nll'):                                         # :44-48
+            with np.errstate(divide='ignore'):
+                a = dt.type(np.log(loss_threshold(loss))) - lpy
+            per, dl = np.maximum(dt.type(0), a), -(a >= 0).astype(dt)
+        else:
+            raise NotImplementedError("Loss : " + loss)
+        g = dl[:, None] * (onehot - p)
+    elif kind == 'ExpLossLayer':                                             # :38-39
+        o = z - z.mean(axis=1, keepdims=True, dtype=dt)
+        per = np.exp(-o[rows, y])
+        g = -per[:, None] * (onehot - one / dt.type(n))
+    elif kind == 'HingeLayer':                                               # :62-64, mean over B*n
+        a = z + one - z[rows, y][:, None]
+        m = (a >= 0).astype(dt)
+        per = (np.maximum(dt.type(0), a)).sum(axis=1, dtype=dt) / dt.type(n)
+        g = (m - onehot * m.sum(axis=1, keepdims=True, dtype=dt)) / dt.type(n)
+    else:
+        raise NotImplementedError(kind)
+    return per.sum(dtype=dt) / dt.type(Bg), (g / dt.type(Bg)).astype(dt)
+
+
+# ----------------------------------------------------------------------------------------------
 # The network -- theanet/neuralnet.py:59-333
 # ----------------------------------------------------------------------------------------------
 def bf16_round(a):
@@ -470,17 +535,24 @@ class OracleNet:
                 if args.get('pdrop', 0):                                     # dropout.py:10
                     L['seed'] = int(rand_gen.randint(1e6)) if rand_gen is not None \
                         else int(np.random.randint(1e6))
-            elif name in ('HiddenLayer', 'SoftmaxLayer'):
+            elif name in ('HiddenLayer',) + OUT_LAYERS:
                 n_in = n_out
                 n_o = args['n_out']
-                actvn = 'softmax' if name == 'SoftmaxLayer' else args.get('actvn', 'relu01')
-                init_act = 'Softmax' if name == 'SoftmaxLayer' else actvn    # outlayers.py:88
+                if name == 'HiddenLayer':
+                    actvn = init_act = args.get('actvn', 'relu01')
+                elif name == 'SoftmaxLayer':
+                    actvn, init_act = 'softmax', 'Softmax'                   # outlayers.py:88
+                    L['loss'] = args.get('loss', 'nll')
+                else:                                                        # outlayers.py:108,132
+                    actvn = init_act = 'linear'
+                    L['loss'] = 'exp' if name == 'ExpLossLayer' else 'hinge' 
                 if wts is None:
                     W, b = init_wb(rand_gen, (n_in, n_o), (n_o,), n_in + n_o, n_in + n_o,
                                    init_act)                                 # hidden.py:21-27
                 else:
                     W, b = [np.asarray(t, np.float32) for t in wts]
                 pdrop = args.get('pdrop', 0) if name == 'HiddenLayer' else 0
+                assert name == 'HiddenLayer' or li == len(layers) - 1, "output layer must be last"
                 if pdrop:                                                    # dropout.py:10
                     L['seed'] = int(rand_gen.randint(1e6)) if rand_gen is not None \
                         else int(np.random.randint(1e6))
@@ -591,13 +663,13 @@ class OracleNet:
                         c['mask'] = m
                     else:                                                    # dropout.py:28-31
                         a = a * dt.type(1 - p)
-            elif kind in ('HiddenLayer', 'SoftmaxLayer'):
+            elif kind in ('HiddenLayer',) + OUT_LAYERS:
                 xin = a.reshape(B, -1)                                       # neuralnet.py:168-169
                 W, b = L['params']
                 z = xin @ W + b
                 c.update(x=xin, z=z, in_shape=a.shape)
-                if kind == 'SoftmaxLayer':
-                    a = log_softmax(z)                                       # logprob (outlayers.py:90-93)
+                if kind in OUT_LAYERS:
+                    c['features'], a, c['probs'] = output_views(kind, z)     # a = the layer's logprob
                 else:
                     a = act_forward(L['actvn'], z)
                     c['a'] = a
@@ -626,7 +698,9 @@ class OracleNet:
         logprob, caches = self._forward(x, True, step, sample0, rand)
         B = logprob.shape[0]
         Bg = B if global_batch is None else global_batch
-        nll = -logprob[np.arange(B), y].sum(dtype=dt) / dt.type(Bg)           # outlayers.py:50-51
+        top = self.spec[-1]
+        nll, g = output_loss(top['kind'], top['loss'], caches[-1]['z'], logprob, y, Bg)
+        self.last_features = caches[-1]['features']
         wtcost = dt.type(0)
         for L in self.spec:                                                  # layer.py:109-117
             if L['reg'] is not None:
@@ -636,16 +710,13 @@ class OracleNet:
                 if l2:
                     wtcost += l2 * sum((t * t).sum(dtype=dt) for t in L['params'])
         cost = nll + wtcost
-        # backward
-        g = np.exp(logprob)
-        g[np.arange(B), y] -= dt.type(1)
-        g = (g / dt.type(Bg)).astype(dt)                                      # dL/dz of the softmax layer
+        # backward: g = dL/dz of the output layer
         grads = [None] * len(self.spec)
         first_weighted = min(i for i, L in enumerate(self.spec) if L['params'])
         for li in range(len(self.spec) - 1, -1, -1):
             L, c = self.spec[li], caches[li]
             kind = L['kind']
-            if kind == 'SoftmaxLayer':
+            if kind in OUT_LAYERS:
                 W, b = L['params']
                 grads[li] = [c['x'].T @ g, g.sum(axis=0)]
                 g = (g @ W.T).reshape(c['in_shape']) if li > first_weighted else None
@@ -696,10 +767,13 @@ class OracleNet:
 
     # -- test twin (neuralnet.py:257-296, outlayers.py:66-80) ---------------------------------------
     def test_step(self, x, y):
-        logprob, _ = self._forward(x, False, 0, 0)
+        """(mean(pred != y), mean(probs[y]), logprob, y_preds): sym_and_oth_err_rate for the
+        non-LOGIT kinds; probs are the raw scores for HingeLayer (outlayers.py:138)."""
+        logprob, caches = self._forward(x, False, 0, 0)
         y = np.asarray(y, np.int64)
         B = logprob.shape[0]
-        probs = np.exp(logprob)
-        y_preds = np.argmax(probs, axis=1)
+        probs = caches[-1]['probs']
+        self.last_features = caches[-1]['features']
+        y_preds = np.argmax(caches[-1]['z'], axis=1)          # argmax of scores = of probs / of o
         return (np.mean(y_preds != y).astype(self.dtype),
                 np.mean(probs[np.arange(B), y], dtype=self.dtype), logprob, y_preds)

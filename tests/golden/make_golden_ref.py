@@ -76,6 +76,30 @@ CASES = {
 }
 
 
+def _small(out_layer, seed):
+    """One conv stage + a tanh hidden layer under the output layer / loss being pinned."""
+    return dict(
+        layers=[
+            ('InputLayer', {'img_sz': 8, 'num_maps': 1}),
+            ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'actvn': 'relu20'}),
+            ('PoolLayer', {'pool_sz': 2}),
+            ('HiddenLayer', {'n_out': 12, 'actvn': 'tanh', 'reg': {'momentum': .5}}),
+            out_layer,
+        ],
+        tp={'SEED': seed, 'BATCH_SZ': 7, 'INIT_LEARNING_RATE': .3, 'EPOCHS_TO_HALF_RATE': 3},
+        channels=1, classes=5, batches=2, steps=5, bump_epoch_at=3)
+
+
+# the other losses and output layers (outlayers.py:38-64,105-147)
+CASES.update({
+    'nllsq': _small(('SoftmaxLayer', {'n_out': 5, 'loss': 'nllsq', 'reg': {'momentum': .5}}), 11),
+    # truncated NLL: threshold .2 = chance level for 5 classes, so rows fall on both sides of it
+    'nll20': _small(('SoftmaxLayer', {'n_out': 5, 'loss': 'nll20', 'reg': {'momentum': .5}}), 12),
+    'exploss': _small(('ExpLossLayer', {'n_out': 5, 'reg': {'momentum': .5, 'L2': 1e-3}}), 13),
+    'hinge': _small(('HingeLayer', {'n_out': 5, 'reg': {'momentum': .5, 'maxnorm': 2.}}), 14),
+})
+
+
 def case_data(name):
     """Deterministic corpus: images in [0,1] whose top third is a flat background that reaches the
     first conv layer as exact zeros, so that exact ties inside pooling windows (A3) and
@@ -207,6 +231,7 @@ def generate(name):
         cost, feats, logprob = train(s % c['batches'])
         rec['cost_%d' % s] = np.float64(cost)
         rec['logprob_%d' % s] = logprob
+        rec['feat_%d' % s] = feats
         store_draws(rec, 's%d' % s, train.draws, c['layers'], base)
     k = 0
     for lyr in net.tr_layers:

@@ -91,6 +91,7 @@ def test_training_steps_match_the_reference_graph(name):
         cost, lp = on.train_step(x[b * B:(b + 1) * B], y[b * B:(b + 1) * B], step=s, rand=rand)
         assert abs(cost - g['cost_%d' % s]) <= TOL_STEP * abs(g['cost_%d' % s]), 'cost, step %d' % s
         assert rel(lp, g['logprob_%d' % s]) < TOL_STEP, 'logprob, step %d' % s
+        assert rel(on.last_features, g['feat_%d' % s]) < TOL_STEP, 'features, step %d' % s
     k = 0
     for L in on.spec:
         for j, t in enumerate(L['params'] or []):
@@ -185,6 +186,7 @@ def test_gpu_training_matches_the_reference_graph(name):
         net.inject = device_draws(MR.rand_table(g, c['layers'], 's%d' % s), torch, net.device)
         cost, feats, lp = fn(s % c['batches'])
         cost, lp = float(cost), np.asarray(lp)
+        assert rel(feats, g['feat_%d' % s]) < TOL_GPU, 'features, step %d' % s
         assert abs(cost - g['cost_%d' % s]) <= TOL_GPU * abs(g['cost_%d' % s]), 'cost, step %d' % s
         assert rel(lp, g['logprob_%d' % s]) < TOL_GPU, 'logprob, step %d' % s
     torch.cuda.synchronize()
@@ -207,7 +209,7 @@ def test_gpu_training_matches_the_reference_graph(name):
     for b in range(c['batches']):
         err, py = test(b)[:2]
         assert abs(err - g['test_%d' % b][0]) < 1e-6
-        assert abs(py - g['test_%d' % b][1]) <= TOL_GPU * g['test_%d' % b][1]
+        assert abs(py - g['test_%d' % b][1]) <= TOL_GPU * abs(g['test_%d' % b][1])
 
 
 @pytest.mark.gpu
@@ -223,4 +225,4 @@ def test_gpu_test_model_matches_the_reference_graph(name):
     for b in range(c['batches']):
         err, py = test(b)[:2]
         assert abs(err - g['test_%d' % b][0]) < 1e-6
-        assert abs(py - g['test_%d' % b][1]) <= TOL_GPU * g['test_%d' % b][1]
+        assert abs(py - g['test_%d' % b][1]) <= TOL_GPU * abs(g['test_%d' % b][1])

@@ -626,3 +626,71 @@ def test_update_all_ranks_l1_l2_frozen(C):
     o = offs[4]
     assert np.array_equal(td.cpu().numpy()[o:o + 550], theta[o:o + 550])
     assert np.array_equal(vd.cpu().numpy()[o:o + 550], vel[o:o + 550])
+
+
+OUT_CASES = [('SoftmaxLayer', 'nllsq'), ('SoftmaxLayer', 'nll20'), ('SoftmaxLayer', 'nll00'),
+             ('SoftmaxLayer', 'nllxx'), ('SoftmaxLayer', 'nll'), ('ExpLossLayer', 'exp'),
+             ('HingeLayer', 'hinge')]
+
+
+@pytest.mark.parametrize('kind,loss', OUT_CASES)
+@pytest.mark.parametrize('B,n', [(7, 5), (64, 10), (33, 457)])
+def test_output_layers_and_losses(C, kind, loss, B, n):
+    """tn_output_loss_fwd_bwd / tn_output_test_stats against the oracle's output_views /
+    output_loss (outlayers.py:38-64,66-80,105-147), which tests/test_golden_ref.py pins to the
+    reference's own graph.  'nll00' = threshold 0 (log = -inf: no row contributes), 'nllxx' =
+    unreadable threshold = plain NLL (outlayers.py:20-27)."""
+    from theanet_b200.layer.outlayers import OUT_KINDS, OutputLayer
+    rng = np.random.default_rng(B * n + len(loss))
+    z = (1.5 * rng.standard_normal((B, n))).astype(np.float32)
+    z[0, :] = 0.25                                  # full tie: argmax = first index, hinge margins all 1
+    ycorp = rng.integers(0, n, B + 5).astype(np.int32)
+    ycorp[5], ycorp[6] = 0, n - 1
+    row0 = 5
+    ctl = make_ctl(C, row0=row0)
+    y = ycorp[row0:row0 + B].astype(np.int64)
+    feat, lp, probs = O.output_views(kind, z)
+    Bg = 2 * B
+    cost, g = O.output_loss(kind, loss, z, lp, y, Bg)
+    lyr = OutputLayer()
+    lyr.loss = loss
+    code, log_thr = lyr.cost()
+    k = OUT_KINDS[{'SoftmaxLayer': 'SOFTMAX', 'ExpLossLayer': 'ExpLoss', 'HingeLayer': 'Hinge'}[kind]]
+    zd, yd = dev(z), dev(ycorp)
+    fd, lpd, gd = (torch.full((B, n), -9., device='cuda') for _ in range(3))
+    rl = torch.zeros(B, device='cuda')
+    C.call('tn_output_loss_fwd_bwd', C.ptr(zd), C.ptr(yd), None, C.ptr(ctl), B, n, k, code, log_thr,
+           1. / Bg, C.ptr(fd), C.ptr(lpd), C.ptr(gd), C.ptr(rl), None)
+    sync()
+    assert rel(fd.cpu().numpy(), feat) < 1e-5
+    assert rel(lpd.cpu().numpy(), lp) < 1e-5
+    assert rel(gd.cpu().numpy(), g) < 1e-5 or (np.abs(g).max() == 0 and gd.abs().max().item() == 0)
+    assert abs(rl.sum().item() / Bg - cost) <= 1e-5 * max(abs(cost), 1e-3)
+    # which rows are active (hinge margins / truncation) is comparison work: exact
+    assert np.array_equal(gd.cpu().numpy() == 0, g == 0)
+    # test twin through the index-list path
+    preds = torch.zeros(B, dtype=torch.int64, device='cuda')
+    stats = torch.zeros(2 + 2 * B, device='cuda')
+    idx = np.arange(row0, row0 + B).astype(np.int32)
+    fd.fill_(-9.)
+    lpd.fill_(-9.)
+    C.call('tn_output_test_stats', C.ptr(zd), C.ptr(yd), C.ptr(dev(idx)), None, B, n, k, C.ptr(fd),
+           C.ptr(lpd), C.ptr(preds), C.ptr(stats), None)
+    sync()
+    want_pred = np.argmax(z, axis=1)
+    assert np.array_equal(preds.cpu().numpy(), want_pred)
+    assert rel(fd.cpu().numpy(), feat) < 1e-5 and rel(lpd.cpu().numpy(), lp) < 1e-5
+    st = stats[:2].cpu().numpy()
+    assert abs(st[0] - np.mean(want_pred != y)) < 1e-6
+    assert abs(st[1] - np.mean(probs[np.arange(B), y])) < 1e-5 * max(1., abs(np.mean(probs[np.arange(B), y])))
+
+
+def test_output_loss_rejects_mismatched_kind_and_loss(C):
+    z = dev(np.zeros((4, 3), np.float32))
+    y = dev(np.zeros(4, np.int32))
+    ctl = make_ctl(C)
+    o = torch.zeros((4, 3), device='cuda')
+    rl = torch.zeros(4, device='cuda')
+    rc = C.lib.tn_output_loss_fwd_bwd(C.ptr(z), C.ptr(y), None, C.ptr(ctl), 4, 3, C.OUT_HINGE,
+                                      C.LOSS_NLL, 0.0, 1.0, C.ptr(o), None, C.ptr(o), C.ptr(rl), None)
+    assert rc == -5 and b'does not take' in C.lib.tn_last_error()      # TN_ERR_UNSUPPORTED

@@ -14,6 +14,8 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libtheanet_b200.so')
 
 # activation / rng enums (include/theanet_b200.h)
 ACT_LINEAR, ACT_RELU, ACT_LEAKY, ACT_TANH, ACT_SCALED_TANH, ACT_SIGMOID, ACT_SOFTPLUS = range(7)
+OUT_SOFTMAX, OUT_EXPLOSS, OUT_HINGE = range(3)                      # TN_OUT_*
+LOSS_NLL, LOSS_NLLSQ, LOSS_NLLTRUNC, LOSS_EXP, LOSS_HINGE = range(5)   # TN_LOSS_*
 CTL_STEP, CTL_SAMPLE0, CTL_ROW0, CTL_LR_BITS, CTL_WORDS = 0, 1, 2, 3, 8
 RNG_DROPOUT, RNG_FLIP, RNG_NOISE, RNG_SCALARS = range(4)
 
@@ -83,6 +85,8 @@ SIGNATURES = {
     'tn_softmax_head_workspace_bytes': (C.c_size_t, [_I, _I, _I]),
     'tn_softmax_head_bwd_weights': (_I, [_P] * 5 + [_I, _I, _I, _P, _P, _P]),
     'tn_softmax_test_stats': (_I, [_P, _P, _P, _P, _I, _I, _P, _P, _P, _P]),
+    'tn_output_loss_fwd_bwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P]),
+    'tn_output_test_stats': (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     'tn_update_workspace_bytes': (C.c_size_t, [_I, _I64]),
     'tn_sgd_momentum_maxnorm_update': (_I, [_P, _P, _P, C.POINTER(ParamSeg), _I, _I64, _P, _F,
                                             _P, _F, _P, _P, _P]),

@@ -4,4 +4,4 @@ from .inlayers import InputLayer, ElasticLayer
 from .convpool import ConvLayer, PoolLayer
 from .dropout import DropOutLayer
 from .hidden import HiddenLayer
-from .outlayers import SoftmaxLayer, OutputLayer
+from .outlayers import SoftmaxLayer, ExpLossLayer, HingeLayer, OutputLayer, OUT_KINDS

@@ -27,7 +27,7 @@ from . import _C
 from . import layer
 from .dist import DistContext
 from .layer import (InputLayer, ElasticLayer, ConvLayer, PoolLayer, DropOutLayer, HiddenLayer,
-                    SoftmaxLayer)
+                    SoftmaxLayer, ExpLossLayer, HingeLayer, OutputLayer, OUT_KINDS)
 
 # ########################### Helper Functions #################################
 
@@ -121,7 +121,7 @@ class NeuralNet():
         self.num_layers += 1
         while self.num_layers < len(layers):
             self.append_next_layer()
-        assert isinstance(self.tr_layers[-1], SoftmaxLayer), "last layer must be a SoftmaxLayer"
+        assert isinstance(self.tr_layers[-1], OutputLayer), "last layer must be an output layer"
 
         if 'CUR_EPOCH' not in training_params:
             training_params['CUR_EPOCH'] = 0
@@ -156,7 +156,7 @@ class NeuralNet():
                                    **layer_args)
         elif curr_layer_type is DropOutLayer:
             curr_layer = DropOutLayer(tr_inpt, self.rand_gen, prev_tr_layer.n_out, **layer_args)
-        elif curr_layer_type in (HiddenLayer, SoftmaxLayer):
+        elif curr_layer_type in (HiddenLayer, SoftmaxLayer, ExpLossLayer, HingeLayer):
             te_inpt = te_inpt.flatten(2)
             curr_layer = curr_layer_type(tr_inpt.flatten(2), wts, self.rand_gen,
                                          prev_tr_layer.n_out, **layer_args)
@@ -244,6 +244,13 @@ class NeuralNet():
         n_out = last.n_out
         self.z = self.out[-1]                                   # pre-softmax scores
         self.logprob = torch.empty((B, n_out), dtype=f32, device=dev)
+        # output stage (outlayers.py): kind of layer, loss; SoftmaxLayer + 'nll' is the hot path
+        self.out_kind = OUT_KINDS[last.kind]
+        self.loss_code, self.log_thr = last.cost()
+        self.plain_nll = self.out_kind == _C.OUT_SOFTMAX and self.loss_code == _C.LOSS_NLL
+        # ExpLossLayer's features are the centred scores, not its log-probabilities
+        self.feat = torch.empty((B, n_out), dtype=f32, device=dev) \
+            if self.out_kind == _C.OUT_EXPLOSS else self.logprob
         self.gsoft = torch.empty((B, n_out), dtype=f32, device=dev)
         self.rowloss = torch.empty(B, dtype=f32, device=dev)
         self.cost = torch.zeros(1, dtype=f32, device=dev)
@@ -251,6 +258,7 @@ class NeuralNet():
         self.preds = torch.zeros(B, dtype=torch.int64, device=dev)
         for l in (last, self.te_layers[-1]):
             l.logprob.tensor = self.logprob
+            l.features.tensor = self.feat
             l.y_preds.tensor = self.preds
         # control block: pinned host copy -> device, refreshed inside the captured graph
         pin = self.device.type == 'cuda'
@@ -296,7 +304,7 @@ class NeuralNet():
                         B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
                 self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
         # classifier head (narrow SoftmaxLayer) on the fused kernels of head.cu
-        self.head = bool(self.fuse_head and self.trainable[-1] and
+        self.head = bool(self.fuse_head and self.trainable[-1] and self.plain_nll and
                          _C.lib.tn_softmax_head_supported(last.n_in, last.n_out))
         if self.head:
             nb = _C.lib.tn_softmax_head_workspace_bytes(B, last.n_in, last.n_out)
@@ -513,7 +521,7 @@ class NeuralNet():
         (prev_out, act code, nn, pkeep, seed, injected mask) or None when layer li has no
         activation of its own."""
         lyr = self.tr_layers[li]
-        if isinstance(lyr, SoftmaxLayer):
+        if isinstance(lyr, OutputLayer):
             return None
         if isinstance(lyr, HiddenLayer):
             pk = 1. - lyr.pdrop if lyr.pdrop else 1.0
@@ -692,9 +700,15 @@ class NeuralNet():
                     _C.ptr(self.gsoft), _C.ptr(self.rowloss),
                     _C.ptr(self.dbuf[li - 1]) if below else None, int(fuse is not None), ac, nn,
                     pk, sd, mi, st)
-        else:
+        elif self.plain_nll:
             _C.call('tn_softmax_nll_fwd_bwd', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
                     _C.ptr(self.ctl), B, n_out, 1.0 / self.batch_sz, _C.ptr(self.logprob),
+                    _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
+        else:                                        # nllsq / nllNN / ExpLossLayer / HingeLayer
+            _C.call('tn_output_loss_fwd_bwd', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
+                    _C.ptr(self.ctl), B, n_out, self.out_kind, self.loss_code, self.log_thr,
+                    1.0 / self.batch_sz, _C.ptr(self.feat),
+                    _C.ptr(self.logprob) if self.feat is not self.logprob else None,
                     _C.ptr(self.gsoft), _C.ptr(self.rowloss), st)
         self._backward()
         self._join_wgrad()
@@ -740,9 +754,16 @@ class NeuralNet():
         B = self.local_bsz
         self.ctl.copy_(self.ctl_host, non_blocking=True)
         self._forward(self.te_layers, False, corpus, idx, labels)
-        _C.call('tn_softmax_test_stats', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
-                _C.ptr(self.ctl), B, self.tr_layers[-1].n_out, _C.ptr(self.logprob),
-                _C.ptr(self.preds), _C.ptr(self.stats), st)
+        if self.out_kind == _C.OUT_SOFTMAX:
+            _C.call('tn_softmax_test_stats', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
+                    _C.ptr(self.ctl), B, self.tr_layers[-1].n_out, _C.ptr(self.logprob),
+                    _C.ptr(self.preds), _C.ptr(self.stats), st)
+        else:
+            _C.call('tn_output_test_stats', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
+                    _C.ptr(self.ctl), B, self.tr_layers[-1].n_out, self.out_kind,
+                    _C.ptr(self.feat),
+                    _C.ptr(self.logprob) if self.feat is not self.logprob else None,
+                    _C.ptr(self.preds), _C.ptr(self.stats), st)
         if self.dist.world > 1:
             self.dist.all_reduce_sum(self.stats[:2])
 
@@ -816,6 +837,18 @@ class NeuralNet():
         h_cost = torch.zeros(1, dtype=torch.float32, pin_memory=self.device.type == 'cuda')
         h_lp = torch.zeros(self.logprob.shape, dtype=torch.float32,
                            pin_memory=self.device.type == 'cuda')
+        two = self.feat is not self.logprob          # ExpLossLayer: features != logprob
+        h_ft = torch.zeros_like(h_lp, pin_memory=self.device.type == 'cuda') if two else None
+
+        def results():
+            """[cost, features, logprob] on the host (neuralnet.py:236-241)."""
+            h_cost.copy_(self.cost, non_blocking=True)
+            h_lp.copy_(self.logprob, non_blocking=True)
+            if two:
+                h_ft.copy_(self.feat, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            lp = h_lp.numpy().copy()
+            return [h_cost.numpy()[0].copy(), h_ft.numpy().copy() if two else lp, lp]
 
         # host-resident corpus: double-buffered minibatch staging.  While step i runs, the H2D copy
         # of batch i+1 (the reference driver walks the batches in order, train.py:210) proceeds on a
@@ -858,12 +891,8 @@ class NeuralNet():
                 fetch(nxt, slot ^ 1)              # overlaps the step that was just enqueued
                 pre['index'], pre['slot'] = nxt, slot ^ 1
                 if lazy:
-                    return self.cost, self.logprob, self.logprob
-                h_cost.copy_(self.cost, non_blocking=True)
-                h_lp.copy_(self.logprob, non_blocking=True)
-                torch.cuda.current_stream(self.device).synchronize()
-                lp = h_lp.numpy().copy()
-                return [h_cost.numpy()[0].copy(), lp, lp]
+                    return self.cost, self.feat, self.logprob
+                return results()
             if take_index_list:
                 ids = np.asarray(indx, dtype=np.int32)[rank * Bl:(rank + 1) * Bl]
                 if host is None:
@@ -886,12 +915,8 @@ class NeuralNet():
             self._train_step(key, xd, idx, yd)
             self.step_count += 1
             if lazy:
-                return self.cost, self.logprob, self.logprob
-            h_cost.copy_(self.cost, non_blocking=True)
-            h_lp.copy_(self.logprob, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            lp = h_lp.numpy().copy()
-            return [h_cost.numpy()[0].copy(), lp, lp]
+                return self.cost, self.feat, self.logprob
+            return results()
 
         return training_fn
 
@@ -917,8 +942,8 @@ class NeuralNet():
             self._run(key, self._test_launches, (xd, None, yd))
             st = self.stats[:2].cpu().numpy() / self.dist.world
             outs = [np.float32(st[0]), np.float32(st[1])]
-            if preds_feats:
-                outs += [self.logprob.cpu().numpy(), self.preds.cpu().numpy()]
+            if preds_feats:                       # features_and_predictions, outlayers.py:66-67
+                outs += [self.feat.cpu().numpy(), self.preds.cpu().numpy()]
             return outs
 
         return test_fn
@@ -937,7 +962,7 @@ class NeuralNet():
             assert xd.shape[0] == Bl, "expected a batch of {} images".format(Bl)
             self._set_ctl(0)
             self._test_launches(xd.reshape((Bl,) + self.tr_layers[0].output.shape), None, yd)
-            outs = [self.logprob.cpu().numpy(), self.preds.cpu().numpy()]
+            outs = [self.feat.cpu().numpy(), self.preds.cpu().numpy()]
             outs += [self.out[i].cpu().numpy() for i in get_output_of_layers]
             return outs
 
