@@ -57,7 +57,7 @@ enum {
 };
 
 /* Philox stream purposes (counter word 3) -- see DESIGN.md "Randomness" */
-enum { TN_RNG_DROPOUT = 0, TN_RNG_FLIP = 1, TN_RNG_NOISE = 2, TN_RNG_SCALARS = 3 };
+enum { TN_RNG_DROPOUT = 0, TN_RNG_FLIP = 1, TN_RNG_NOISE = 2, TN_RNG_SCALARS = 3, TN_RNG_COLOR = 4 };
 
 int tn_version(void);
 const char *tn_last_error(void);
@@ -120,6 +120,21 @@ size_t tn_conv2d_wgrad_workspace_bytes(int B, int C, int S, int M, int f);
  * `workspace` (>= tn_conv2d_wgrad_workspace_bytes). */
 int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float *db, void *workspace, int B,
                     int C, int S, int M, int f, int pad_lo, int out_sz, void *stream);
+
+/* ---- MeanLayer (theanet/layer/convpool.py:129-144): out[plane] = mean over the S x S map --------- */
+int tn_meanpool_fwd(const float *x, float *out, int planes, int S, void *stream);
+/* dx[plane,i] = dout[plane] / (S*S) * act'(x[plane,i]); x = output of the layer below (NULL or
+ * act = linear: no activation derivative), so it yields dL/dz of a ConvLayer below directly. */
+int tn_meanpool_bwd(const float *dout, const float *x, float *dx, int planes, int S, int act,
+                    int act_nn, void *stream);
+
+/* ---- ColorLayer (theanet/layer/color.py:9-52): random white balance + two gamma curves per
+ * (sample, map): out = maxval * (1 - (1 - clip(x/maxval * e1, 0, 1)^e2)^e3), e1 = exp(log_balance*u1),
+ * e2 = exp(log_gamma*u2), e3 = exp(log_gamma*u3), u ~ U(-1,1) from the (seed, step, global sample)
+ * stream (block = map) or from u_inj (B*C*3 float32).  log_* = float32(ln balance / gamma). */
+int tn_color_jitter(const float *x, float *out, int B, int C, int S, float log_balance,
+                    float log_gamma, float maxval, uint64_t seed, const int32_t *ctl,
+                    const float *u_inj, void *stream);
 
 /* ---- ConvLayer + PoolLayer fused (small channel counts: theanet's shipped networks) ----------
  * One image per CTA stays resident in shared memory; f must be 3 or 5.  pool = 0: no PoolLayer

@@ -28,6 +28,7 @@ PURPOSE_DROPOUT = 0
 PURPOSE_FLIP = 1
 PURPOSE_NOISE = 2
 PURPOSE_SCALARS = 3
+PURPOSE_COLOR = 4
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -105,3 +106,9 @@ def elastic_scalars(seed, step):
     """8 float32 uniforms in (0,1): [trans_y, trans_x, origin_y, origin_x, zoom_y, zoom_x, angle, spare]."""
     w = random_words(seed, PURPOSE_SCALARS, step, [0], 8)[0]
     return uniform01(w).astype(np.float32)
+
+
+def color_uniforms(seed, step, samples, maps):
+    """ColorLayer draws: (len(samples), maps, 3) float32 in (-1,1); block = map, words x, y, z."""
+    w = random_words(seed, PURPOSE_COLOR, step, samples, 4 * maps).reshape(len(samples), maps, 4)
+    return (2.0 * uniform01(w[:, :, :3]) - 1.0).astype(np.float32)

@@ -383,6 +383,27 @@ class InjectedRandom:
 
 
 # ----------------------------------------------------------------------------------------------
+# ColorLayer -- theanet/layer/color.py:9-52
+# ----------------------------------------------------------------------------------------------
+def color_jitter(x, prm, u):
+    """u: (B, maps, 3) float32 draws in (-1,1) -- balance, gamma, gamma (pos_rand is called three
+    times, color.py:32-42).  np.log(a) enters the graph as a floatX constant; everything float32."""
+    f32 = np.float32
+    maxval = f32(prm.get('maxval', 1))
+    lb, lg = f32(np.log(prm.get('balance', 1))), f32(np.log(prm.get('gamma', 1)))
+    u = np.asarray(u, f32)
+    e1 = np.exp(lb * u[:, :, 0])[:, :, None, None]
+    e2 = np.exp(lg * u[:, :, 1])[:, :, None, None]
+    e3 = np.exp(lg * u[:, :, 2])[:, :, None, None]
+    out = x.astype(f32) / maxval
+    out = out * e1
+    out = np.clip(out, f32(0), f32(1))
+    out = out ** e2
+    out = f32(1) - (f32(1) - out) ** e3
+    return (out * maxval).astype(x.dtype)
+
+
+# ----------------------------------------------------------------------------------------------
 # Output layers and losses -- theanet/layer/outlayers.py:12-147
 # ----------------------------------------------------------------------------------------------
 OUT_LAYERS = ('SoftmaxLayer', 'ExpLossLayer', 'HingeLayer')
@@ -531,6 +552,22 @@ class OracleNet:
                 out_sz = pool_out_size(out_sz, args['pool_sz'], args.get('ignore_border', False))
                 n_out = num_maps * out_sz ** 2
                 L['num_maps'], L['out_sz'] = num_maps, out_sz
+            elif name == 'MeanLayer':                                        # convpool.py:129-144
+                L['in_sz'] = out_sz
+                out_sz, n_out = 1, num_maps
+                L['num_maps'], L['out_sz'] = num_maps, out_sz
+            elif name == 'ColorLayer':                                       # color.py:9-52
+                if li > 0:
+                    args['num_maps'], args['img_sz'] = num_maps, out_sz     # neuralnet.py:132-142
+                num_maps = args.get('num_maps', 3)
+                out_sz = args['img_sz']
+                n_out = num_maps * out_sz ** 2
+                L['identity'] = args.get('gamma', 1) == 1 and args.get('balance', 1) == 1
+                if not L['identity']:
+                    assert args.get('gamma', 1) > 0 and args.get('balance', 1) > 0
+                    L['seed'] = int(rand_gen.randint(1e6)) if rand_gen is not None \
+                        else int(np.random.randint(1e6))                     # color.py:30
+                L['num_maps'], L['out_sz'] = num_maps, out_sz
             elif name == 'DropOutLayer':
                 if args.get('pdrop', 0):                                     # dropout.py:10
                     L['seed'] = int(rand_gen.randint(1e6)) if rand_gen is not None \
@@ -575,6 +612,8 @@ class OracleNet:
             L['tc'] = False
             if bf16 and L['kind'] == 'ConvLayer':
                 nxt = self.spec[li + 1] if li + 1 < len(self.spec) else None
+                if nxt is not None and nxt['kind'] == 'MeanLayer':
+                    continue                                # stays float32 in the product as well
                 pool = nxt['args'] if nxt is not None and nxt['kind'] == 'PoolLayer' else None
                 in_sz = self.spec[li - 1].get('out_sz')
                 L['tc'] = conv_tc_eligible(
@@ -649,6 +688,16 @@ class OracleNet:
             elif kind == 'PoolLayer':
                 a, pc = pool_forward(a, args['pool_sz'], args.get('ignore_border', False))
                 c['pc'] = pc
+            elif kind == 'MeanLayer':
+                c['in_shape'] = a.shape
+                a = a.sum(axis=(2, 3), dtype=dt) / dt.type(a.shape[2] * a.shape[3])
+            elif kind == 'ColorLayer':
+                if train and not L['identity']:
+                    if rand is not None and (li, 'color') in rand:
+                        u = np.asarray(rand[(li, 'color')], np.float32)
+                    else:
+                        u = philox.color_uniforms(L['seed'], step, samples, a.shape[1])
+                    a = color_jitter(a, args, u.reshape(B, a.shape[1], 3))
             elif kind == 'DropOutLayer':
                 p = args.get('pdrop', 0)
                 if p:
@@ -733,6 +782,13 @@ class OracleNet:
             elif kind == 'PoolLayer':
                 if g is not None:
                     g = pool_backward(g, c['pc'])
+            elif kind == 'MeanLayer':
+                if g is not None:
+                    _, _, h_, w_ = c['in_shape']
+                    g = np.broadcast_to((g / dt.type(h_ * w_))[:, :, None, None], c['in_shape']).astype(dt)
+            elif kind == 'ColorLayer':
+                assert li <= first_weighted, "no gradient through ColorLayer is implemented"
+                g = None
             elif kind == 'ConvLayer':
                 W, b = L['params']
                 gz = act_backward(L['actvn'], c['z'], c['a'], g)

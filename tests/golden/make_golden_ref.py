@@ -90,8 +90,42 @@ def _small(out_layer, seed):
         channels=1, classes=5, batches=2, steps=5, bump_epoch_at=3)
 
 
-# the other losses and output layers (outlayers.py:38-64,105-147)
+# the other losses and output layers (outlayers.py:38-64,105-147), MeanLayer, ColorLayer
 CASES.update({
+    'meanpool': dict(
+        layers=[
+            ('InputLayer', {'img_sz': 8, 'num_maps': 2}),
+            ('ConvLayer', {'num_maps': 4, 'filter_sz': 3, 'stride': 1, 'mode': 'same', 'actvn': 'relu10',
+                           'reg': {'momentum': .6}}),
+            ('MeanLayer', {}),
+            ('HiddenLayer', {'n_out': 6, 'actvn': 'tanh', 'reg': {'momentum': .6}}),
+            ('SoftmaxLayer', {'n_out': 3, 'reg': {'momentum': .6}}),
+        ],
+        tp={'SEED': 21, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .4, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=2, classes=3, batches=2, steps=5, bump_epoch_at=2),
+    # ColorLayer as the input layer ...
+    'color0': dict(
+        layers=[
+            ('ColorLayer', {'img_sz': 8, 'num_maps': 3, 'balance': 1.5, 'gamma': 1.4}),
+            ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'actvn': 'relu',
+                           'reg': {'momentum': .6}}),
+            ('PoolLayer', {'pool_sz': 2}),
+            ('SoftmaxLayer', {'n_out': 4, 'reg': {'momentum': .6}}),
+        ],
+        tp={'SEED': 22, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .2, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=3, classes=4, batches=2, steps=4, bump_epoch_at=2),
+    # ... and behind an ElasticLayer, with a value range of [0, 2] (maxval)
+    'color1': dict(
+        layers=[
+            ('ElasticLayer', {'img_sz': 8, 'num_maps': 3, 'translation': 1}),
+            ('ColorLayer', {'balance': 1.2, 'gamma': 1.6, 'maxval': 2}),
+            ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'actvn': 'relu',
+                           'reg': {'momentum': .6}}),
+            ('PoolLayer', {'pool_sz': 2}),
+            ('SoftmaxLayer', {'n_out': 4, 'reg': {'momentum': .6}}),
+        ],
+        tp={'SEED': 23, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .2, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=3, classes=4, batches=2, steps=4, bump_epoch_at=2),
     'nllsq': _small(('SoftmaxLayer', {'n_out': 5, 'loss': 'nllsq', 'reg': {'momentum': .5}}), 11),
     # truncated NLL: threshold .2 = chance level for 5 classes, so rows fall on both sides of it
     'nll20': _small(('SoftmaxLayer', {'n_out': 5, 'loss': 'nll20', 'reg': {'momentum': .5}}), 12),
@@ -140,15 +174,21 @@ def draw_keys(layers):
         elif kind in ('DropOutLayer', 'HiddenLayer') and a.get('pdrop', 0):
             out.append((stream, 0, li, 'mask'))
             stream += 1
+        elif kind == 'ColorLayer' and not (a.get('gamma', 1) == 1 and a.get('balance', 1) == 1):
+            for k in range(3):                      # pos_rand: balance, gamma, gamma (color.py:36-42)
+                out.append((stream, k, li, 'color%d' % k))
+            stream += 1
     return out
 
 
 def rand_table(g, layers, prefix):
     """Rebuild the oracle's injected-randomness dict for one call from the arrays stored in g."""
-    rand, u = {}, {}
+    rand, u, col = {}, {}, {}
     for _, _, li, key in draw_keys(layers):
         v = g['%s_%d_%s' % (prefix, li, key)]
-        if key in ('flip', 'mask'):
+        if key.startswith('color'):
+            col.setdefault(li, [None] * 3)[int(key[-1])] = v
+        elif key in ('flip', 'mask'):
             shape = tuple(g['%s_%d_%s_shape' % (prefix, li, key)])
             rand[(li, key)] = np.unpackbits(v)[:int(np.prod(shape))].reshape(shape).astype(np.float32)
         elif key == 'noise':
@@ -158,6 +198,8 @@ def rand_table(g, layers, prefix):
     for li, d in u.items():
         rand[(li, 'u')] = d
         rand.setdefault((li, 'noise'), None)
+    for li, d in col.items():
+        rand[(li, 'color')] = np.stack(d, axis=-1)           # (B, maps, 3)
     return rand
 
 
@@ -243,7 +285,7 @@ def generate(name):
     for b in range(c['batches']):
         err, py = test(b)
         rec['test_%d' % b] = np.array([err, py], np.float64)
-    if c['layers'][0][0] == 'ElasticLayer':                        # tests/test_elastic.py's view
+    if c['layers'][0][0] == 'ElasticLayer' and 'magnitude' in c['layers'][0][1]:   # tests/test_elastic.py's view
         el = theano.function([net.x], net.tr_layers[0].debugout[:2])
         img, disp = el(x[:B])
         rec['elastic_img'], rec['elastic_disp'] = img, disp

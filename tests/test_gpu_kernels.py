@@ -694,3 +694,54 @@ def test_output_loss_rejects_mismatched_kind_and_loss(C):
     rc = C.lib.tn_output_loss_fwd_bwd(C.ptr(z), C.ptr(y), None, C.ptr(ctl), 4, 3, C.OUT_HINGE,
                                       C.LOSS_NLL, 0.0, 1.0, C.ptr(o), None, C.ptr(o), C.ptr(rl), None)
     assert rc == -5 and b'does not take' in C.lib.tn_last_error()      # TN_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize('planes,S,act', [(12, 8, 'relu10'), (300, 13, 'tanh'), (5, 1, 'linear'),
+                                          (64, 32, 'relu')])
+def test_meanpool_fwd_bwd(C, planes, S, act):
+    """MeanLayer (convpool.py:129-144): mean over each map; backward spreads g / S^2 and applies
+    the activation derivative of the layer below."""
+    rng = np.random.default_rng(planes + S)
+    z = rng.standard_normal((planes, S, S)).astype(np.float32)
+    a = O.act_forward(act, z)
+    g = rng.standard_normal(planes).astype(np.float32)
+    want = a.sum(axis=(1, 2), dtype=np.float32) / np.float32(S * S)
+    want_dx = O.act_backward(act, z, a, np.broadcast_to((g / np.float32(S * S))[:, None, None], a.shape))
+    ad, gd = dev(a), dev(g)
+    out = torch.zeros(planes, device='cuda')
+    dx = torch.full((planes, S, S), -3., device='cuda')
+    C.call('tn_meanpool_fwd', C.ptr(ad), C.ptr(out), planes, S, None)
+    C.call('tn_meanpool_bwd', C.ptr(gd), C.ptr(ad), C.ptr(dx), planes, S, *C.act_code(act), None)
+    sync()
+    assert rel(out.cpu().numpy(), want) < 1e-6
+    assert rel(dx.cpu().numpy(), want_dx) < 1e-6
+    C.call('tn_meanpool_bwd', C.ptr(gd), None, C.ptr(dx), planes, S, 0, 0, None)   # nothing fused
+    sync()
+    assert np.array_equal(dx.cpu().numpy(),
+                          np.broadcast_to((g / np.float32(S * S))[:, None, None], a.shape))
+
+
+@pytest.mark.parametrize('B,Cm,S,balance,gamma,maxval', [(6, 3, 8, 1.5, 1.4, 1.), (33, 1, 28, 1., 2., 255.),
+                                                         (4, 5, 64, 2., 1., 2.)])
+def test_color_jitter(C, B, Cm, S, balance, gamma, maxval):
+    """ColorLayer (color.py:9-52) on its Philox stream and with injected draws, against the
+    oracle's color_jitter / philox.color_uniforms."""
+    rng = np.random.default_rng(B + S)
+    x = (rng.random((B, Cm, S, S)) * maxval).astype(np.float32)
+    x[0, 0, 0, :4] = [0., maxval, 2 * maxval, -1.]             # clip on both sides, exact 0 and 1
+    seed, step, s0 = 4711, 9, 40
+    ctl = make_ctl(C, step=step, sample0=s0)
+    prm = {'balance': balance, 'gamma': gamma, 'maxval': maxval}
+    u = philox.color_uniforms(seed, step, np.arange(s0, s0 + B), Cm)
+    assert u.shape == (B, Cm, 3) and np.all(np.abs(u) < 1)
+    want = O.color_jitter(x, prm, u)
+    lb, lg = float(np.float32(np.log(balance))), float(np.float32(np.log(gamma)))
+    xd = dev(x)
+    out = torch.full_like(xd, -5.)
+    C.call('tn_color_jitter', C.ptr(xd), C.ptr(out), B, Cm, S, lb, lg, maxval, seed, C.ptr(ctl), None, None)
+    sync()
+    assert rel(out.cpu().numpy(), want) < 1e-5
+    u2 = rng.uniform(-1, 1, (B, Cm, 3)).astype(np.float32)
+    C.call('tn_color_jitter', C.ptr(xd), C.ptr(xd), B, Cm, S, lb, lg, maxval, 0, None, C.ptr(dev(u2)), None)
+    sync()                                                         # in place, injected draws
+    assert rel(xd.cpu().numpy(), O.color_jitter(x, prm, u2)) < 1e-5

@@ -76,6 +76,9 @@ SIGNATURES = {
     'tn_dense_bwd_data': (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _D, _U64, _P, _P, _P]),
     'tn_dense_bwd_weights': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'tn_set_dense_mode': (_I, [_I]),
+    'tn_meanpool_fwd': (_I, [_P, _P, _I, _I, _P]),
+    'tn_meanpool_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    'tn_color_jitter': (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _U64, _P, _P, _P]),
     'tn_dropout_apply': (_I, [_P, _P, _I, _I, _D, _U64, _P, _P, _F, _P]),
     'tn_act_bwd': (_I, [_P, _P, _P, _I64, _I, _I, _P]),
     'tn_softmax_nll_fwd_bwd': (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),

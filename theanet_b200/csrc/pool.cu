@@ -51,9 +51,60 @@ __global__ void maxpool_bwd_kernel(const float *__restrict__ dout, const float *
   }
 }
 
+// ---- MeanLayer (theanet/layer/convpool.py:129-144): tt.mean(x, axis=(2,3)) ----------------------
+// one warp per (sample, map) plane; fixed-order lane-strided sums + shuffle tree (deterministic)
+__global__ void meanpool_fwd_kernel(const float *__restrict__ x, float *__restrict__ out,
+                                    int planes, int hw) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int p = blockIdx.x * wpb + (threadIdx.x >> 5); p < planes; p += gridDim.x * wpb) {
+    const float *src = x + (size_t)p * hw;
+    float s = 0.f;
+    for (int i = lane; i < hw; i += 32) s += src[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[p] = __fdiv_rn(s, (float)hw);       // sum / count, as Theano's mean
+  }
+}
+
+// dx[plane, i] = dout[plane] / (S*S) * act'(x[plane, i]); x = the output of the layer below
+__global__ void meanpool_bwd_kernel(const float *__restrict__ dout, const float *__restrict__ x,
+                                    float *__restrict__ dx, uint32_t total, FastDiv32 divhw,
+                                    float hw, ActK ak) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t plane = divhw.div(t);
+    const float g = __fdiv_rn(dout[plane], hw);
+    dx[t] = x ? g * act_bwd_k(ak, x[t]) : g;
+  }
+}
+
 }  // namespace tn
 
 using namespace tn;
+
+extern "C" int tn_meanpool_fwd(const float *x, float *out, int planes, int S, void *stream) {
+  TN_REQUIRE(x && out, TN_ERR_ARG, "tn_meanpool_fwd: null argument");
+  TN_REQUIRE(planes > 0 && S > 0, TN_ERR_SHAPE, "tn_meanpool_fwd: bad shape planes=%d S=%d", planes, S);
+  const int wpb = 8;
+  const int blocks = (int)min64(ceil_div64(planes, wpb), (int64_t)kNumSM * 8);
+  meanpool_fwd_kernel<<<blocks, wpb * 32, 0, (cudaStream_t)stream>>>(x, out, planes, S * S);
+  TN_LAUNCH_CHECK("tn_meanpool_fwd");
+  return TN_OK;
+}
+
+extern "C" int tn_meanpool_bwd(const float *dout, const float *x, float *dx, int planes, int S,
+                               int act, int act_nn, void *stream) {
+  TN_REQUIRE(dout && dx, TN_ERR_ARG, "tn_meanpool_bwd: null argument");
+  TN_REQUIRE(planes > 0 && S > 0, TN_ERR_SHAPE, "tn_meanpool_bwd: bad shape");
+  const int64_t total = (int64_t)planes * S * S;
+  TN_REQUIRE(total < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_meanpool_bwd: tensor too large");
+  const int threads = 256;
+  const int blocks = (int)min64(ceil_div64(total, threads), (int64_t)kNumSM * 32);
+  meanpool_bwd_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+      dout, x, dx, (uint32_t)total, FastDiv32(S * S), (float)(S * S), make_actk(act, act_nn));
+  TN_LAUNCH_CHECK("tn_meanpool_bwd");
+  return TN_OK;
+}
 
 extern "C" int tn_maxpool_fwd(const float *x, float *out, int planes, int S, int p, int out_sz,
                               void *stream) {

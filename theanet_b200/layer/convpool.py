@@ -74,3 +74,21 @@ class PoolLayer(Layer):
 
     def TestVersion(self, inpt):
         return PoolLayer(inpt, *self.args)
+
+
+class MeanLayer(Layer):
+    """Global average over each map (reference: theanet/layer/convpool.py:129-144):
+    (B, maps, S, S) -> (B, maps)."""
+
+    def __init__(self, inpt, num_maps, in_sz):
+        self.params = []
+        self.inpt = inpt
+        self.num_maps = num_maps
+        self.in_sz = in_sz
+        self.out_sz = 1
+        self.n_out = num_maps
+        self.output = Out(self, (num_maps,))
+        self.representation = "Mean Maps:{:2d} Output:{:2d}".format(num_maps, self.out_sz)
+
+    def TestVersion(self, inpt):
+        return MeanLayer(inpt, self.num_maps, self.in_sz)

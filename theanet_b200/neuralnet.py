@@ -26,8 +26,9 @@ import torch
 from . import _C
 from . import layer
 from .dist import DistContext
-from .layer import (InputLayer, ElasticLayer, ConvLayer, PoolLayer, DropOutLayer, HiddenLayer,
-                    SoftmaxLayer, ExpLossLayer, HingeLayer, OutputLayer, OUT_KINDS)
+from .layer import (InputLayer, ElasticLayer, ColorLayer, ConvLayer, PoolLayer, MeanLayer,
+                    DropOutLayer, HiddenLayer, SoftmaxLayer, ExpLossLayer, HingeLayer, OutputLayer,
+                    OUT_KINDS)
 
 # ########################### Helper Functions #################################
 
@@ -114,8 +115,8 @@ class NeuralNet():
 
         # Input Layer
         input_layer_type = getattr(layer, layers[0][0])
-        assert input_layer_type in (InputLayer, ElasticLayer), \
-            "First layer needs to be Input or Elastic Layer"
+        assert input_layer_type in (InputLayer, ElasticLayer, ColorLayer), \
+            "First layer needs to be Input or Elastic or Color Layer"
         self.tr_layers.append(input_layer_type(None, rand_gen=self.rand_gen, **layers[0][1]))
         self.te_layers.append(self.tr_layers[0].TestVersion(None))
         self.num_layers += 1
@@ -142,15 +143,23 @@ class NeuralNet():
         tr_inpt, te_inpt = prev_tr_layer.output, prev_te_layer.output
         curr_layer_type = getattr(layer, layer_type, None)
 
-        if curr_layer_type in (ConvLayer, PoolLayer):
+        if curr_layer_type in (ColorLayer, ConvLayer, PoolLayer, MeanLayer):
             # a DropOutLayer carries no map geometry: look through it (neuralnet.py:123-130)
             use = self.tr_layers[self.num_layers - 2] if type(prev_tr_layer) is DropOutLayer \
                 else prev_tr_layer
             num_prev_maps, prev_out_sz = use.num_maps, use.out_sz
 
-        if curr_layer_type is ConvLayer:
+        if curr_layer_type is ColorLayer:                     # neuralnet.py:132-142
+            layer_args.pop("num_maps", None)
+            layer_args.pop("img_sz", None)
+            curr_layer = ColorLayer(tr_inpt, num_maps=num_prev_maps, img_sz=prev_out_sz,
+                                    rand_gen=self.rand_gen, **layer_args)
+        elif curr_layer_type is ConvLayer:
             curr_layer = ConvLayer(tr_inpt, wts, self.rand_gen, self.batch_sz, num_prev_maps,
                                    prev_out_sz, **layer_args)
+        elif curr_layer_type is MeanLayer:
+            curr_layer = MeanLayer(tr_inpt, num_maps=num_prev_maps, in_sz=prev_out_sz,
+                                   **layer_args)
         elif curr_layer_type is PoolLayer:
             curr_layer = PoolLayer(tr_inpt, num_maps=num_prev_maps, in_sz=prev_out_sz,
                                    **layer_args)
@@ -334,6 +343,8 @@ class NeuralNet():
         nxt = self.tr_layers[li + 1] if li + 1 < len(self.tr_layers) else None
         if lyr.mode != 'same' or lyr.act.code not in (_C.ACT_LINEAR, _C.ACT_RELU, _C.ACT_LEAKY):
             return None
+        if isinstance(nxt, MeanLayer):                # float32 path: its backward fuses act' itself
+            return None
         if isinstance(nxt, PoolLayer) and (nxt.pool_sz != 2 or lyr.out_sz % 2 or nxt.ignore_border):
             return None
         C_, S, M, f, O = lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.out_sz
@@ -430,7 +441,20 @@ class NeuralNet():
                 break                                 # scores are computed by the fused head
             out = self.out[li]
             x = self.out[li - 1] if li else None
-            if isinstance(lyr, (InputLayer, ElasticLayer)):
+            if isinstance(lyr, ColorLayer):
+                C_, h = lyr.num_maps, lyr.out_sz
+                if li == 0:       # batch loader first (tn_elastic_warp mode 0 = gather the rows)
+                    _C.call('tn_elastic_warp', _C.ptr(corpus), idxp, ctl, B, C_, h, 0, 0, None,
+                            None, 0.0, None, 0, _C.ptr(out), st)
+                    x = out
+                if train and not lyr.identity:
+                    _C.call('tn_color_jitter', _C.ptr(x), _C.ptr(out), B, C_, h, lyr.log_balance,
+                            lyr.log_gamma, float(lyr.maxval), lyr.seed, ctl,
+                            self._inj(li, 'color'), st)
+                elif li:                                  # identity twin: plain copy
+                    _C.call('tn_dropout_apply', _C.ptr(x), _C.ptr(out), B, C_ * h * h, 1.0, 0, ctl,
+                            None, 1.0, st)
+            elif isinstance(lyr, (InputLayer, ElasticLayer)):
                 if li:
                     raise NotImplementedError("input-type layers past position 0")
                 # geometry from the TRAIN twin: the reference's Elastic test twin does not forward
@@ -499,6 +523,8 @@ class NeuralNet():
             elif isinstance(lyr, PoolLayer):
                 _C.call('tn_maxpool_fwd', _C.ptr(x), _C.ptr(out), B * lyr.num_maps, lyr.in_sz,
                         lyr.pool_sz, lyr.out_sz, st)
+            elif isinstance(lyr, MeanLayer):
+                _C.call('tn_meanpool_fwd', _C.ptr(x), _C.ptr(out), B * lyr.num_maps, lyr.in_sz, st)
             elif isinstance(lyr, DropOutLayer):
                 n = x[0].numel()
                 if train and lyr.pdrop:
@@ -654,6 +680,17 @@ class NeuralNet():
                             nn, st)
                     if fuse and fuse[3] < 1.0:
                         raise NotImplementedError("dropout-masked dense output feeding a pool")
+            elif isinstance(lyr, MeanLayer):
+                if below:
+                    po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, _C.ACT_LINEAR, 0)
+                    _C.call('tn_meanpool_bwd', _C.ptr(g), _C.ptr(po), _C.ptr(dx), B * lyr.num_maps,
+                            lyr.in_sz, ac, nn, st)
+                    if fuse and fuse[3] < 1.0:
+                        raise NotImplementedError("dropout-masked dense output feeding a MeanLayer")
+            elif isinstance(lyr, ColorLayer):
+                if below:
+                    raise NotImplementedError("ColorLayer above a trainable layer (no gradient "
+                                              "through the colour curves is implemented)")
             elif isinstance(lyr, DropOutLayer):
                 if below:
                     n = x[0].numel()
