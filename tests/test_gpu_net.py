@@ -285,3 +285,40 @@ def test_cifar3conv_bf16_tensor_core_stack_matches_oracle():
     e, pr = net.get_test_model(x, y)(0)
     oe, opr, _, _ = on.test_step(x[:B], y[:B])
     assert abs(e - oe) < 1e-6 and abs(pr - opr) <= TOL_BF16 * opr
+
+
+@pytest.mark.parametrize('use_graph', [True, False])
+def test_exact_resume_with_momentum_step_and_stream_seeds(tmp_path, use_graph):
+    """The reference's .pkl carries weights only: a resumed run starts with zero momentum and new
+    random streams.  get_resume_state()/set_resume_state() add the momentum
+    buffers, the step counter and the stream seeds: 3 + 3 steps across a pickle round trip are
+    bit-identical to 6 steps in one go (elastic field, flip noise and dropout masks included)."""
+    from theanet_b200.neuralnet import NeuralNet
+    prms = load_prms('mnist.prms', 16, 28)
+    x, y = synth(64, 1, 28, 10)
+    p1, p2 = copy.deepcopy(prms), copy.deepcopy(prms)
+    ref = NeuralNet(p1['layers'], p1['training_params'], use_graph=use_graph)
+    f_ref = ref.get_trin_model(x, y)
+    want = [f_ref(i % 4) for i in range(6)]
+    net = NeuralNet(p2['layers'], p2['training_params'], use_graph=use_graph)
+    f = net.get_trin_model(x, y)
+    for i in range(3):
+        f(i % 4)
+    pkl = tmp_path / 'resume.pkl'
+    with open(pkl, 'wb') as fh:
+        pickle.dump(dict(net.get_init_params(), resume=net.get_resume_state()), fh, -1)
+    with open(pkl, 'rb') as fh:
+        saved = pickle.load(fh)
+    net2 = NeuralNet(saved['layers'], saved['training_params'], saved['allwts'], use_graph=use_graph)
+    net2.set_resume_state(saved['resume'])
+    f2 = net2.get_trin_model(x, y)
+    for i in range(3, 6):
+        cost, feats, lp = f2(i % 4)
+        assert cost == want[i][0] and np.array_equal(lp, want[i][2])
+    for a, b in zip(net2.get_init_params()['allwts'], ref.get_init_params()['allwts']):
+        for t, u in zip(a, b):
+            assert np.array_equal(t, u)
+    # without the resume state the weights carry over but momentum and streams do not
+    net3 = NeuralNet(saved['layers'], saved['training_params'], saved['allwts'], use_graph=use_graph)
+    cost3 = net3.get_trin_model(x, y)(3)[0]
+    assert cost3 != want[3][0]

@@ -1010,6 +1010,27 @@ class NeuralNet():
                 "training_params": self.tr_prms,
                 "allwts": [l.get_wts() for l in self.tr_layers]}
 
+    # -- exact resume (the reference's .pkl drops momentum and RNG state) ----------
+    def get_resume_state(self):
+        """What ``get_init_params()`` does not carry: the momentum buffers (layer.py:78-80 keeps
+        them only inside the compiled graph), the step counter and the per-layer stream seeds that
+        key the Philox draws.  ``set_resume_state`` on a net built from the same .pkl continues the
+        run bit for bit; a .pkl without it resumes like the reference does (fresh momentum, new
+        random streams)."""
+        return {"velocities": self.get_velocities(), "step_count": int(self.step_count),
+                "seeds": [getattr(l, 'seed', None) for l in self.tr_layers]}
+
+    def set_resume_state(self, state):
+        assert len(state["velocities"]) == len(self.tr_layers) == len(state["seeds"])
+        for lyr, vels, seed in zip(self.tr_layers, state["velocities"], state["seeds"]):
+            assert len(vels) == len(lyr.params)
+            for p, v in zip(lyr.params, vels):
+                p.vel.copy_(torch.as_tensor(np.asarray(v, np.float32)).reshape(p.vel.shape))
+            if seed is not None:
+                lyr.seed = seed
+        self.step_count = int(state["step_count"])
+        self._graphs = {}            # captured graphs bake the seeds in as kernel arguments
+
     def set_rate(self):
         self.cur_learn_rate.set_value(
             self.tr_prms['INIT_LEARNING_RATE'] /

@@ -107,6 +107,8 @@ def main(argv):
 
     print("\nInitializing the net ... ")
     net = nn.NeuralNet(layers, tr_prms, allwts)
+    if params.get('resume') is not None:          # written by this driver: momentum, step, seeds
+        net.set_resume_state(params['resume'])
     print(net)
     print(net.get_wts_info(detailed=True).replace("\n\t", ""))
 
@@ -130,7 +132,8 @@ def main(argv):
             os.remove(saved[0])
         saved[0] = head + '_{:02.0f}.pkl'.format(te[0])
         with open(saved[0], 'wb') as f:
-            pickle.dump(net.get_init_params(), f, -1)
+            # the reference's schema (neuralnet.py:298-301) + one extra key for an exact resume
+            pickle.dump(dict(net.get_init_params(), resume=net.get_resume_state()), f, -1)
 
     print("Training ...")
     print("Epoch   Cost  Tr_Error Tr_{0}    Te_Error Te_{0}".format(aux_name))
