@@ -82,6 +82,9 @@ typedef struct tn_elastic_prm {
   int zoom_on;        /* zoom != 1 */
   int nearest;        /* 1: iround gather (inlayers.py:124-127), 0: bilinear (:129-137) */
   double clip_hi;     /* h - 1 - .001 (inlayers.py:121-122) */
+  int step_offset;    /* the draws are those of step ctl[TN_CTL_STEP] + step_offset: 1 computes the
+                         NEXT step's field while the current step is still running */
+  int reserved;
 } tn_elastic_prm;
 
 /* noise[2*h*h] ~ N(0,1) float32, Box-Muller on the (seed, step) Philox stream (inlayers.py:94) */

@@ -322,3 +322,35 @@ def test_exact_resume_with_momentum_step_and_stream_seeds(tmp_path, use_graph):
     net3 = NeuralNet(saved['layers'], saved['training_params'], saved['allwts'], use_graph=use_graph)
     cost3 = net3.get_trin_model(x, y)(3)[0]
     assert cost3 != want[3][0]
+
+
+def test_field_prefetch_survives_alternating_corpora_and_test_calls():
+    """Under CUDA graphs the elastic field of step s+1 is computed on a side branch of step s
+    (NeuralNet._train_step).  Alternating two compiled training functions, test calls in between
+    and a learning-rate change must give the eager sequence bit for bit."""
+    from theanet_b200.neuralnet import NeuralNet
+    prms = load_prms('mnist.prms', 16, 28)
+    xa, ya = synth(64, 1, 28, 10, seed=1)
+    xb, yb = synth(64, 1, 28, 10, seed=2)
+
+    def run(use_graph):
+        p = copy.deepcopy(prms)
+        net = NeuralNet(p['layers'], p['training_params'], use_graph=use_graph)
+        assert net.field_prefetch == use_graph
+        fa, fb = net.get_trin_model(xa, ya), net.get_trin_model(xb, yb)
+        te = net.get_test_model(xb, yb)
+        out = []
+        for s in range(7):
+            f = fa if s % 3 else fb
+            out.append(f(s % 4)[0])
+            if s == 2:
+                out.append(te(1)[1])
+            if s == 4:
+                net.inc_epoch_set_rate()
+        return out, net.get_init_params()['allwts']
+
+    (c_g, w_g), (c_e, w_e) = run(True), run(False)
+    assert c_g == c_e
+    for a, b in zip(w_g, w_e):
+        for t, u in zip(a, b):
+            assert np.array_equal(t, u)

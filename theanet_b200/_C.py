@@ -23,7 +23,8 @@ RNG_DROPOUT, RNG_FLIP, RNG_NOISE, RNG_SCALARS = range(4)
 class ElasticPrm(C.Structure):
     _fields_ = [('h', C.c_int), ('sigma', C.c_int), ('translation', C.c_float),
                 ('magnitude', C.c_float), ('log_zoom', C.c_float), ('angle_rad', C.c_float),
-                ('zoom_on', C.c_int), ('nearest', C.c_int), ('clip_hi', C.c_double)]
+                ('zoom_on', C.c_int), ('nearest', C.c_int), ('clip_hi', C.c_double),
+                ('step_offset', C.c_int), ('reserved', C.c_int)]
 
 
 class ParamSeg(C.Structure):

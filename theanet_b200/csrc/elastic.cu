@@ -72,7 +72,7 @@ __global__ void elastic_field_kernel(tn_elastic_prm prm, const float *__restrict
       for (int i = threadIdx.x; i < 2 * hw; i += blockDim.x)
         s_el[i] = __fmul_rn(prm.magnitude, noise[i]);
     } else {   // draw the field here (every CTA needs all of it): one launch less per step
-      const uint32_t step = (uint32_t)ctl[TN_CTL_STEP];
+      const uint32_t step = (uint32_t)(ctl[TN_CTL_STEP] + prm.step_offset);
       for (int t = threadIdx.x; 4 * t < 2 * hw; t += blockDim.x) {
         float z[4];
         noise_block(seed, step, t, z);
@@ -87,7 +87,7 @@ __global__ void elastic_field_kernel(tn_elastic_prm prm, const float *__restrict
     if (u_inj) {
       for (int i = 0; i < 8; ++i) u[i] = u_inj[i];
     } else {
-      const uint32_t step = (uint32_t)ctl[TN_CTL_STEP];
+      const uint32_t step = (uint32_t)(ctl[TN_CTL_STEP] + prm.step_offset);
       const Philox4 a = philox_block(seed, TN_RNG_SCALARS, step, 0u, 0u);
       const Philox4 b = philox_block(seed, TN_RNG_SCALARS, step, 0u, 1u);
       const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};

@@ -281,8 +281,12 @@ class NeuralNet():
         if isinstance(l0, ElasticLayer) and not l0.identity:
             h = l0.img_sz
             self.el_noise = torch.zeros(2 * h * h, dtype=f32, device=dev)
-            self.el_gidx = torch.zeros(h * h, dtype=torch.int32, device=dev)
-            self.el_gfrac = torch.zeros(2 * h * h, dtype=f32, device=dev)
+            # two sets of sampling grids: under CUDA graphs the field of step s+1 is computed on a
+            # side branch while step s runs (it depends on (seed, step) only), see _train_launches
+            self.el_grids = [(torch.zeros(h * h, dtype=torch.int32, device=dev),
+                              torch.zeros(2 * h * h, dtype=f32, device=dev)) for _ in range(2)]
+            self.el_gidx, self.el_gfrac = self.el_grids[0]
+            self._field_step = None          # step whose field sits in el_grids[step & 1]
             self.el_target = torch.zeros(2 * h * h, dtype=torch.float64, device=dev)
             self.el_tyx = torch.zeros(2 * h * h, dtype=torch.float64, device=dev)
             self.el_filt = torch.from_numpy(l0.filt).to(dev) if l0.filt is not None else None
@@ -294,7 +298,14 @@ class NeuralNet():
             prm.angle_rad = float(np.float32(l0.angle * np.pi / 180))
             prm.nearest = int(bool(l0.nearest))
             prm.clip_hi = h - 1 - .001
+            prm.step_offset = 0
             self.el_prm = prm
+            nxt = _C.ElasticPrm.from_buffer_copy(prm)
+            nxt.step_offset = 1
+            self.el_prm_next = nxt
+        self.field_prefetch = (os.environ.get('TN_FIELD_PREFETCH', '1') == '1' and self.use_graph
+                               and isinstance(l0, ElasticLayer) and not l0.identity
+                               and l0.has_grid)
         # workspaces; conv_fused[li]: ConvLayer li (+ the PoolLayer right above it) runs on the
         # fused small-channel kernels (conv_fused.cu)
         self.ws = {}
@@ -465,15 +476,13 @@ class NeuralNet():
                 if train and isinstance(lyr, ElasticLayer) and not lyr.identity:
                     seed = lyr.seed
                     if lyr.has_grid:
-                        noise = self._inj(0, 'noise')     # None: drawn inside tn_elastic_field
-                        dbg = self.debug_elastic
-                        _C.call('tn_elastic_field', ctypes.byref(self.el_prm), noise,
-                                self._inj(0, 'u'), _C.ptr(self.el_filt), seed, ctl,
-                                _C.ptr(self.el_target) if dbg else None,
-                                _C.ptr(self.el_tyx) if dbg else None,
-                                _C.ptr(self.el_gidx), _C.ptr(self.el_gfrac), st)
+                        if self._prefetching():           # computed during the previous step
+                            g_i, g_f = self.el_grids[self.step_count & 1]
+                        else:
+                            g_i, g_f = self.el_gidx, self.el_gfrac
+                            self._launch_field(self.el_prm, g_i, g_f, st)
                         mode = 1 if lyr.nearest else 2
-                        gidx, gfrac = _C.ptr(self.el_gidx), _C.ptr(self.el_gfrac)
+                        gidx, gfrac = _C.ptr(g_i), _C.ptr(g_f)
                     pflip = float(lyr.pflip)
                 _C.call('tn_elastic_warp', _C.ptr(corpus), idxp, ctl, B, C_, h, invert, mode, gidx,
                         gfrac, pflip, self._inj(0, 'flip') if train else None, seed, _C.ptr(out),
@@ -541,6 +550,18 @@ class NeuralNet():
                         float(lyr.test_scale), st)
             else:
                 raise NotImplementedError(type(lyr).__name__)
+
+    def _prefetching(self):
+        return (self.field_prefetch and self.use_graph and not self.inject
+                and not self.debug_elastic)
+
+    def _launch_field(self, prm, g_i, g_f, st):
+        lyr = self.tr_layers[0]
+        dbg = self.debug_elastic
+        _C.call('tn_elastic_field', ctypes.byref(prm), self._inj(0, 'noise'), self._inj(0, 'u'),
+                _C.ptr(self.el_filt), lyr.seed, _C.ptr(self.ctl),
+                _C.ptr(self.el_target) if dbg else None, _C.ptr(self.el_tyx) if dbg else None,
+                _C.ptr(g_i), _C.ptr(g_f), st)
 
     def _fuse_info(self, li):
         """How a consumer turns dL/d(out[li]) into dL/dz of layer li inside its own epilogue:
@@ -724,6 +745,10 @@ class NeuralNet():
         if idx is not None:
             self.idx.copy_(self.idx_host, non_blocking=True)
         self._forward(self.tr_layers, True, corpus, idx, labels)
+        if self._prefetching():       # next step's sampling grid, off the critical path
+            g_i, g_f = self.el_grids[(self.step_count + 1) & 1]
+            with self._wgrad_stream() as sw:
+                self._launch_field(self.el_prm_next, g_i, g_f, sw)
         last = self.tr_layers[-1]
         n_out = last.n_out
         if self.head:
@@ -772,6 +797,16 @@ class NeuralNet():
         """One training step.  Single GPU: one CUDA graph.  Data parallel: graph (forward +
         backward) -> NCCL all-reduce of the flat gradient buffer -> graph (update); set
         TN_GRAPH_NCCL=1 to capture the collective inside a single graph instead."""
+        prefetch = self._prefetching()
+        if prefetch:
+            # the graph of step s reads the sampling grid from el_grids[s & 1] and, on a side
+            # branch, fills el_grids[(s+1) & 1] for the next step: one graph per parity
+            if self._field_step != self.step_count:      # first step, or the sequence was broken
+                self.ctl.copy_(self.ctl_host, non_blocking=True)
+                g_i, g_f = self.el_grids[self.step_count & 1]
+                self._launch_field(self.el_prm, g_i, g_f, self._stream())
+            key = key + ('f%d' % (self.step_count & 1),)
+            self._field_step = self.step_count + 1
         if self.dp_fused:
             parity = self.step_count & 1              # graphs bake pointers: one per parity
             self._bind_grads(parity)
@@ -1029,6 +1064,7 @@ class NeuralNet():
             if seed is not None:
                 lyr.seed = seed
         self.step_count = int(state["step_count"])
+        self._field_step = None
         self._graphs = {}            # captured graphs bake the seeds in as kernel arguments
 
     def set_rate(self):
