@@ -247,7 +247,7 @@ def store_draws(rec, prefix, draws, layers, base):
     assert len(seen) == len(table), "a random variable of the graph was never evaluated"
 
 
-def generate(name):
+def generate(name, write=True):
     theano, tt, NeuralNet = _import_reference()
     from theano.tensor.shared_randomstreams import RandomStreams
     c = CASES[name]
@@ -291,11 +291,33 @@ def generate(name):
         rec['elastic_img'], rec['elastic_disp'] = img, disp
         store_draws(rec, 'el', [d for d in el.draws], c['layers'][:1], base)
     path = os.path.join(HERE, 'ref_%s.npz' % name)
+    if not write:
+        return rec
     np.savez_compressed(path, **rec)
     print('%-6s -> %s (%.0f KB)  cost %s' % (name, os.path.relpath(path, ROOT), os.path.getsize(path) / 1024,
                                              ' '.join('%.5f' % rec['cost_%d' % s] for s in range(c['steps']))))
 
 
+def check(name):
+    """Re-run the reference for one case and compare with the committed fixture."""
+    rec = generate(name, write=False)
+    g = np.load(os.path.join(HERE, 'ref_%s.npz' % name))
+    assert sorted(rec) == sorted(g.files), "fixture keys differ"
+    for k in g.files:
+        a, b = np.asarray(rec[k]), g[k]
+        assert a.shape == b.shape, k
+        if a.dtype.kind == 'f':
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-7), k
+        else:
+            assert np.array_equal(a, b), k
+    print('%s: fixture reproduced from %s' % (name, REFERENCE))
+
+
 if __name__ == '__main__':
-    for n in (sys.argv[1:] or CASES):
-        generate(n)
+    args = sys.argv[1:]
+    if args and args[0] == '--check':
+        for n in (args[1:] or CASES):
+            check(n)
+    else:
+        for n in (args or CASES):
+            generate(n)

@@ -226,3 +226,14 @@ def test_gpu_test_model_matches_the_reference_graph(name):
         err, py = test(b)[:2]
         assert abs(err - g['test_%d' % b][0]) < 1e-6
         assert abs(py - g['test_%d' % b][1]) <= TOL_GPU * abs(g['test_%d' % b][1])
+
+
+@pytest.mark.skipif(not os.path.isdir(MR.REFERENCE), reason="the reference checkout only exists in the build container")
+def test_fixtures_are_what_the_reference_computes_here():
+    """Provenance: re-run the reference's own code (in a subprocess, so its stand-in `theano`
+    module never enters this test process) and compare with the committed ref_*.npz."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(GOLD, 'make_golden_ref.py'), '--check', 'plain', 'mixed',
+                        'hinge'], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.count('fixture reproduced') == 3
