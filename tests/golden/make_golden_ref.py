@@ -257,6 +257,15 @@ def generate(name, write=True):
     base = len(RandomStreams.instances)
     net = NeuralNet(layers, tp)                                    # the reference's constructor
     rec = {'x': x, 'y': y}
+    # what the reference prints (train.py:115-116,139-140): layer representations of both twins,
+    # the layer / training-parameter listings (after the constructor mutated them) and the
+    # weight summary -- the drop-in must print the same text
+    rec['repr'] = np.array(str(net).split('\nParams')[0])
+    rec['layers_info'] = np.array(net.get_layers_info())
+    rec['tp_info'] = np.array(net.get_training_params_info())
+    rec['wts_info'] = np.array(net.get_wts_info(detailed=True))
+    rec['shapes'] = np.array([[getattr(l, 'n_out', -1), getattr(l, 'num_maps', -1) or -1,
+                               getattr(l, 'out_sz', -1) or -1] for l in net.tr_layers])
     k = 0
     for lyr in net.tr_layers:
         for p in lyr.params:
