@@ -114,6 +114,19 @@ CASES.update({
         ],
         tp={'SEED': 22, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .2, 'EPOCHS_TO_HALF_RATE': 2},
         channels=3, classes=4, batches=2, steps=4, bump_epoch_at=2),
+    # ... in front of an ElasticLayer (Elastic past position 0, neuralnet.py:132-142) ...
+    'color_el': dict(
+        layers=[
+            ('ColorLayer', {'img_sz': 9, 'num_maps': 2, 'balance': 1.3, 'gamma': 1.2}),
+            ('ElasticLayer', {'translation': 1, 'zoom': 1.2, 'magnitude': 10, 'sigma': 2, 'pflip': .05,
+                              'angle': 8}),
+            ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'actvn': 'relu',
+                           'reg': {'momentum': .6}}),
+            ('PoolLayer', {'pool_sz': 2}),
+            ('SoftmaxLayer', {'n_out': 4, 'reg': {'momentum': .6}}),
+        ],
+        tp={'SEED': 24, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .2, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=2, classes=4, batches=2, steps=4, bump_epoch_at=2),
     # ... and behind an ElasticLayer, with a value range of [0, 2] (maxval)
     'color1': dict(
         layers=[

@@ -143,17 +143,17 @@ class NeuralNet():
         tr_inpt, te_inpt = prev_tr_layer.output, prev_te_layer.output
         curr_layer_type = getattr(layer, layer_type, None)
 
-        if curr_layer_type in (ColorLayer, ConvLayer, PoolLayer, MeanLayer):
+        if curr_layer_type in (ElasticLayer, ColorLayer, ConvLayer, PoolLayer, MeanLayer):
             # a DropOutLayer carries no map geometry: look through it (neuralnet.py:123-130)
             use = self.tr_layers[self.num_layers - 2] if type(prev_tr_layer) is DropOutLayer \
                 else prev_tr_layer
             num_prev_maps, prev_out_sz = use.num_maps, use.out_sz
 
-        if curr_layer_type is ColorLayer:                     # neuralnet.py:132-142
+        if curr_layer_type in (ElasticLayer, ColorLayer):     # neuralnet.py:132-142
             layer_args.pop("num_maps", None)
             layer_args.pop("img_sz", None)
-            curr_layer = ColorLayer(tr_inpt, num_maps=num_prev_maps, img_sz=prev_out_sz,
-                                    rand_gen=self.rand_gen, **layer_args)
+            curr_layer = curr_layer_type(tr_inpt, num_maps=num_prev_maps, img_sz=prev_out_sz,
+                                         rand_gen=self.rand_gen, **layer_args)
         elif curr_layer_type is ConvLayer:
             curr_layer = ConvLayer(tr_inpt, wts, self.rand_gen, self.batch_sz, num_prev_maps,
                                    prev_out_sz, **layer_args)
@@ -277,8 +277,14 @@ class NeuralNet():
         self.idx_host = torch.zeros(B, dtype=torch.int32, pin_memory=pin)
         self.idx = torch.zeros(B, dtype=torch.int32, device=dev)
         # elastic scratch
-        l0 = self.tr_layers[0]
-        if isinstance(l0, ElasticLayer) and not l0.identity:
+        # the (single) distorting ElasticLayer: normally layer 0, possibly behind a Color / Input layer
+        els = [i for i, l in enumerate(self.tr_layers) if isinstance(l, ElasticLayer) and not l.identity]
+        if len(els) > 1:
+            raise NotImplementedError("more than one distorting ElasticLayer")
+        self.el_index = els[0] if els else None
+        self.idx_iota = torch.arange(B, dtype=torch.int32, device=dev)   # rows of an in-flight batch
+        l0 = self.tr_layers[self.el_index] if els else None
+        if l0 is not None:
             h = l0.img_sz
             self.el_noise = torch.zeros(2 * h * h, dtype=f32, device=dev)
             # two sets of sampling grids: under CUDA graphs the field of step s+1 is computed on a
@@ -304,8 +310,7 @@ class NeuralNet():
             nxt.step_offset = 1
             self.el_prm_next = nxt
         self.field_prefetch = (os.environ.get('TN_FIELD_PREFETCH', '1') == '1' and self.use_graph
-                               and isinstance(l0, ElasticLayer) and not l0.identity
-                               and l0.has_grid)
+                               and l0 is not None and l0.has_grid)
         # workspaces; conv_fused[li]: ConvLayer li (+ the PoolLayer right above it) runs on the
         # fused small-channel kernels (conv_fused.cu)
         self.ws = {}
@@ -466,11 +471,14 @@ class NeuralNet():
                     _C.call('tn_dropout_apply', _C.ptr(x), _C.ptr(out), B, C_ * h * h, 1.0, 0, ctl,
                             None, 1.0, st)
             elif isinstance(lyr, (InputLayer, ElasticLayer)):
-                if li:
-                    raise NotImplementedError("input-type layers past position 0")
+                if li and isinstance(lyr, InputLayer):
+                    raise NotImplementedError("InputLayer past position 0")
+                # layer 0 gathers its rows from the corpus; further up the source is the batch
+                # the layer below produced (rows 0..B-1)
+                src, rows = (_C.ptr(corpus), idxp) if li == 0 else (_C.ptr(x), _C.ptr(self.idx_iota))
                 # geometry from the TRAIN twin: the reference's Elastic test twin does not forward
                 # num_maps (inlayers.py:157-163), harmless there because it is elementwise
-                C_, h = self.tr_layers[0].num_maps, lyr.out_sz
+                C_, h = self.tr_layers[li].num_maps, lyr.out_sz
                 invert = int(getattr(lyr, 'invert', False))
                 mode, gidx, gfrac, pflip, seed = 0, None, None, 0.0, 0
                 if train and isinstance(lyr, ElasticLayer) and not lyr.identity:
@@ -484,8 +492,8 @@ class NeuralNet():
                         mode = 1 if lyr.nearest else 2
                         gidx, gfrac = _C.ptr(g_i), _C.ptr(g_f)
                     pflip = float(lyr.pflip)
-                _C.call('tn_elastic_warp', _C.ptr(corpus), idxp, ctl, B, C_, h, invert, mode, gidx,
-                        gfrac, pflip, self._inj(0, 'flip') if train else None, seed, _C.ptr(out),
+                _C.call('tn_elastic_warp', src, rows, ctl, B, C_, h, invert, mode, gidx,
+                        gfrac, pflip, self._inj(li, 'flip') if train else None, seed, _C.ptr(out),
                         st)
             elif isinstance(lyr, ConvLayer) and li in self.conv_tc:
                 t = self.conv_tc[li]
@@ -556,9 +564,10 @@ class NeuralNet():
                 and not self.debug_elastic)
 
     def _launch_field(self, prm, g_i, g_f, st):
-        lyr = self.tr_layers[0]
+        li = self.el_index
+        lyr = self.tr_layers[li]
         dbg = self.debug_elastic
-        _C.call('tn_elastic_field', ctypes.byref(prm), self._inj(0, 'noise'), self._inj(0, 'u'),
+        _C.call('tn_elastic_field', ctypes.byref(prm), self._inj(li, 'noise'), self._inj(li, 'u'),
                 _C.ptr(self.el_filt), lyr.seed, _C.ptr(self.ctl),
                 _C.ptr(self.el_target) if dbg else None, _C.ptr(self.el_tyx) if dbg else None,
                 _C.ptr(g_i), _C.ptr(g_f), st)
@@ -708,10 +717,10 @@ class NeuralNet():
                             lyr.in_sz, ac, nn, st)
                     if fuse and fuse[3] < 1.0:
                         raise NotImplementedError("dropout-masked dense output feeding a MeanLayer")
-            elif isinstance(lyr, ColorLayer):
+            elif isinstance(lyr, (ColorLayer, ElasticLayer)):
                 if below:
-                    raise NotImplementedError("ColorLayer above a trainable layer (no gradient "
-                                              "through the colour curves is implemented)")
+                    raise NotImplementedError("{} above a trainable layer (no gradient through "
+                                              "it is implemented)".format(type(lyr).__name__))
             elif isinstance(lyr, DropOutLayer):
                 if below:
                     n = x[0].numel()
@@ -1100,7 +1109,7 @@ class NeuralNet():
     def elastic_debugout(self):
         """[displacement (2,h,h) float64, clipped coordinates (2,h,h)] of the last training step
         (needs ``debug_elastic = True``), cf. ElasticLayer.debugout (inlayers.py:145-155)."""
-        h = self.tr_layers[0].img_sz
+        h = self.tr_layers[self.el_index].img_sz
         tgt = self.el_target.cpu().numpy().reshape(2, h, h)
         return [tgt - np.indices((h, h)), self.el_tyx.cpu().numpy().reshape(2, h, h)]
 
