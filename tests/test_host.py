@@ -135,3 +135,22 @@ def test_product_never_imports_the_oracle():
         files += [os.path.join(d, f) for f in fs if f.endswith('.py')]
     for f in files:
         assert not bad.search(open(f).read()), f
+
+
+def test_train_driver_helpers():
+    """train.py: rotating test windows (reference train.py:170-176), epoch batch order, image
+    reshaping (reference train.py:22-34)."""
+    import train
+    w = train.window_indices(1000, 100, 300)
+    assert [next(w) for _ in range(4)] == [[0, 1, 2], [3, 4, 5], [6, 7, 8], [9, 0, 1]]
+    assert train.epoch_batches(105, 10) == list(range(10))
+    rs = np.random.RandomState(3)
+    b = train.epoch_batches(105, 10, rs)
+    flat = np.concatenate(b)
+    assert len(b) == 10 and all(v.dtype == np.int32 and len(v) == 10 for v in b)
+    assert len(set(flat.tolist())) == 100 and flat.max() < 105
+    assert train.as_images(np.zeros((5, 64))).shape == (5, 1, 8, 8)
+    assert train.as_images(np.zeros((5, 8, 8))).shape == (5, 1, 8, 8)
+    assert train.as_images(np.zeros((5, 3, 8, 8))).shape == (5, 3, 8, 8)
+    with pytest.raises(ValueError):
+        train.as_images(np.zeros((5, 63)))

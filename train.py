@@ -72,6 +72,16 @@ def window_indices(total, batch_sz, window):
         cur = (cur + each) % n_all
 
 
+def epoch_batches(n, batch_sz, rng=None):
+    """What one epoch feeds the training function: batch indices 0..n//B-1 in order (train.py:210),
+    or, with a RandomState, n//B index vectors of a fresh permutation (remainder dropped)."""
+    nb = n // batch_sz
+    if rng is None:
+        return list(range(nb))
+    perm = rng.permutation(n)[:nb * batch_sz].astype(np.int32)
+    return [perm[i * batch_sz:(i + 1) * batch_sz] for i in range(nb)]
+
+
 def percent_errors(pairs):
     pairs = list(pairs)
     return tuple(100 * float(np.mean([p[k] for p in pairs])) for k in (0, 1))
@@ -113,7 +123,12 @@ def main(argv):
     print(net.get_wts_info(detailed=True).replace("\n\t", ""))
 
     print("\nCompiling ... ")
-    training_fn = net.get_trin_model(trin_x, data.training_y)
+    # 'SHUFFLE': True (an extension; the reference's TODO:14-16 asks for it) draws a fresh
+    # permutation of the training set every epoch and feeds index lists (neuralnet.py:228-234);
+    # the default walks the batches in their fixed order like the reference (train.py:210)
+    shuffle = bool(tr_prms.get('SHUFFLE', False))
+    training_fn = net.get_trin_model(trin_x, data.training_y, take_index_list=shuffle)
+    order_rng = np.random.RandomState(tr_prms['SEED'] + 1)
     test_fn_tr = net.get_test_model(trin_x, data.training_y)
     test_fn_te = net.get_test_model(test_x, data.testing_y)
 
@@ -139,8 +154,9 @@ def main(argv):
     print("Epoch   Cost  Tr_Error Tr_{0}    Te_Error Te_{0}".format(aux_name))
     for epoch in range(n_epochs):
         total_cost = 0.
-        for ibatch in range(n_tr // B):                     # remainder dropped, fixed order
-            cost, features, logprobs = training_fn(ibatch)
+        batches = epoch_batches(n_tr, B, order_rng if shuffle else None)
+        for ibatch, rows in enumerate(batches):             # remainder dropped
+            cost, features, logprobs = training_fn(rows)
             total_cost += cost
             if np.isnan(total_cost):
                 print(net.get_wts_info(detailed=True))
