@@ -57,7 +57,7 @@ enum {
 };
 
 /* Philox stream purposes (counter word 3) -- see DESIGN.md "Randomness" */
-enum { TN_RNG_DROPOUT = 0, TN_RNG_FLIP = 1, TN_RNG_NOISE = 2, TN_RNG_SCALARS = 3, TN_RNG_COLOR = 4 };
+enum { TN_RNG_DROPOUT = 0, TN_RNG_FLIP = 1, TN_RNG_NOISE = 2, TN_RNG_SCALARS = 3, TN_RNG_COLOR = 4, TN_RNG_AUX = 5 };
 
 int tn_version(void);
 const char *tn_last_error(void);
@@ -138,6 +138,20 @@ int tn_meanpool_bwd(const float *dout, const float *x, float *dx, int planes, in
 int tn_color_jitter(const float *x, float *out, int B, int C, int S, float log_balance,
                     float log_gamma, float maxval, uint64_t seed, const int32_t *ctl,
                     const float *u_inj, void *stream);
+
+/* ---- auxiliary-input layers (theanet/layer/auxiliary.py:14-160) ------------------------------
+ * LocationInfo input: aux (B,2,2) -> loc (B,2).  train != 0: aux[b,0,:]*u + aux[b,1,:]*(1-u) with
+ * u ~ U(0,1) per sample from the (seed, step, global sample) stream or u_inj (B) (:25-28);
+ * train == 0: mean over axis 1 (:31).  Both times boost (:33).  The two small dense layers that
+ * follow (:36-53) and every gradient use tn_dense_*. */
+int tn_aux_location_mix(const float *aux, float *loc, int B, float boost, int train, uint64_t seed,
+                        const int32_t *ctl, const float *u_inj, void *stream);
+/* out (B, na+nc) = [a (B,na) | c (B,nc)]  (AuxConcatLayer, :80) */
+int tn_concat_cols(const float *a, int na, const float *c, int nc, float *out, int B, void *stream);
+/* out (B,n) = src[:, off:off+n] of a (B,stride) matrix (gradient of the concatenation) */
+int tn_slice_cols(const float *src, int stride, int off, int n, float *out, int B, void *stream);
+/* dst[i] += src[i]  (SoftAuxLayer scores: hidden + cross term, :133-134) */
+int tn_add_inplace(float *dst, const float *src, int64_t n, void *stream);
 
 /* ---- ConvLayer + PoolLayer fused (small channel counts: theanet's shipped networks) ----------
  * One image per CTA stays resident in shared memory; f must be 3 or 5.  pool = 0: no PoolLayer

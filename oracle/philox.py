@@ -29,6 +29,7 @@ PURPOSE_FLIP = 1
 PURPOSE_NOISE = 2
 PURPOSE_SCALARS = 3
 PURPOSE_COLOR = 4
+PURPOSE_AUX = 5
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):
@@ -112,3 +113,9 @@ def color_uniforms(seed, step, samples, maps):
     """ColorLayer draws: (len(samples), maps, 3) float32 in (-1,1); block = map, words x, y, z."""
     w = random_words(seed, PURPOSE_COLOR, step, samples, 4 * maps).reshape(len(samples), maps, 4)
     return (2.0 * uniform01(w[:, :, :3]) - 1.0).astype(np.float32)
+
+
+def aux_uniforms(seed, step, samples):
+    """LocationInfo mixing weights: one float32 uniform in (0,1) per sample (block 0, word x)."""
+    w = random_words(seed, PURPOSE_AUX, step, samples, 1)[:, 0]
+    return uniform01(w).astype(np.float32)

@@ -598,6 +598,39 @@ class OracleNet:
                 L['reg'] = dict(DEFAULT_REG, **dict(args.get('reg', ())))
                 n_out = n_o
                 num_maps, out_sz = None, None
+            elif name in ('AuxConcatLayer', 'SoftAuxLayer'):                 # auxiliary.py:60-160
+                n_in = n_out
+                nh, no = args['n_aux']
+                assert args['aux_type'] == 'LocationInfo'
+                ws = None if wts is None else [np.asarray(t, np.float32) for t in wts]
+                hidden = []
+                if name == 'SoftAuxLayer':                                   # :108-111
+                    n_o = args['n_out']
+                    hidden = list(init_wb(rand_gen, (n_in, n_o), (n_o,), n_in + n_o, n_in + n_o,
+                                          'linear')) if ws is None else ws[:2]
+                    aux_ws = None if ws is None else ws[2:6]
+                else:
+                    aux_ws = ws
+                if rand_gen is not None:                                     # :25 (stream first)
+                    L['seed'] = int(rand_gen.randint(1e6))
+                else:
+                    L['seed'] = int(np.random.randint(1e6))
+                if aux_ws is None:                                           # :36-53
+                    aux_ws = list(init_wb(rand_gen, (2, nh), nh, nh + 2, nh + 2, 'relu50')) + \
+                        list(init_wb(rand_gen, (nh, no), no, no + nh, no + nh, 'relu01'))
+                cross = []
+                if name == 'SoftAuxLayer':                                   # :121-126
+                    cross = list(init_wb(rand_gen, (no, n_o), n_o, no + n_o, no + n_o,
+                                         'softmax')) if ws is None else ws[6:]
+                    L['reg'] = dict(DEFAULT_REG, **dict(args.get('reg', ())))
+                    L['loss'] = args.get('loss', 'nll')
+                    n_out = n_o
+                    assert li == len(layers) - 1, "output layer must be last"
+                else:                                                        # no reg: never updated
+                    n_out = n_in + no
+                L.update(pdrop=0, boost=args.get('boost', 1), n_in=n_in)
+                L['params'] = [t.astype(self.dtype) for t in hidden + aux_ws + cross]
+                num_maps, out_sz = None, None
             else:
                 raise NotImplementedError("Unknown Layer Type" + name)
             L['n_out'] = n_out
@@ -640,7 +673,7 @@ class OracleNet:
         return [[p.astype(np.float32) for p in L['params']] for L in self.spec]
 
     # -- forward --------------------------------------------------------------------------------
-    def _forward(self, x, train, step, sample0, rand=None):
+    def _forward(self, x, train, step, sample0, rand=None, aux=None):
         dt = self.dtype
         a = np.asarray(x, dt)
         B = a.shape[0]
@@ -712,6 +745,35 @@ class OracleNet:
                         c['mask'] = m
                     else:                                                    # dropout.py:28-31
                         a = a * dt.type(1 - p)
+            elif kind in ('AuxConcatLayer', 'SoftAuxLayer'):
+                assert aux is not None, "Auxillary data not supplied"
+                xin = a.reshape(B, -1)
+                P = L['params']
+                k0 = 2 if kind == 'SoftAuxLayer' else 0
+                w1, b1, w2, b2 = P[k0:k0 + 4]
+                A = np.asarray(aux, dt).reshape(B, 2, 2)
+                if train:                                                    # auxiliary.py:25-28
+                    if rand is not None and (li, 'auxu') in rand:
+                        u = np.asarray(rand[(li, 'auxu')], np.float32)
+                    else:
+                        u = philox.aux_uniforms(L['seed'], step, samples)
+                    u = u.astype(dt).reshape(B, 1)
+                    loc = A[:, 0, :] * u + A[:, 1, :] * (dt.type(1) - u)
+                else:                                                        # :31
+                    loc = (A[:, 0, :] + A[:, 1, :]) / dt.type(2)
+                loc = loc * dt.type(L['boost'])                              # :33
+                z1 = loc @ w1 + b1
+                hid = act_forward('relu50', z1)
+                z2 = hid @ w2 + b2
+                feat = act_forward('relu01', z2)
+                c.update(x=xin, in_shape=a.shape, loc=loc, z1=z1, hid=hid, z2=z2, aux=feat)
+                if kind == 'AuxConcatLayer':                                 # :80
+                    a = np.concatenate([xin, feat], axis=1)
+                else:                                                        # :133-134
+                    W, b, cw, cb = P[0], P[1], P[6], P[7]
+                    z = ((xin @ W + b) + cb) + feat @ cw
+                    c['z'] = z
+                    c['features'], a, c['probs'] = output_views('SoftmaxLayer', z)
             elif kind in ('HiddenLayer',) + OUT_LAYERS:
                 xin = a.reshape(B, -1)                                       # neuralnet.py:168-169
                 W, b = L['params']
@@ -739,16 +801,18 @@ class OracleNet:
         return a, caches
 
     # -- one training step (neuralnet.py:203-241, layer.py:70-117) --------------------------------
-    def train_step(self, x, y, step=0, sample0=0, rand=None, global_batch=None, apply_update=True):
+    def train_step(self, x, y, step=0, sample0=0, rand=None, global_batch=None, apply_update=True,
+                   aux=None):
         """Returns (cost, logprob).  ``global_batch`` (default: len(x)) is the divisor of the mean
         NLL so that a data-parallel shard contributes its share of the global-batch gradient."""
         dt = self.dtype
         y = np.asarray(y, np.int64)
-        logprob, caches = self._forward(x, True, step, sample0, rand)
+        logprob, caches = self._forward(x, True, step, sample0, rand, aux)
         B = logprob.shape[0]
         Bg = B if global_batch is None else global_batch
         top = self.spec[-1]
-        nll, g = output_loss(top['kind'], top['loss'], caches[-1]['z'], logprob, y, Bg)
+        top_kind = 'SoftmaxLayer' if top['kind'] == 'SoftAuxLayer' else top['kind']
+        nll, g = output_loss(top_kind, top['loss'], caches[-1]['z'], logprob, y, Bg)
         self.last_features = caches[-1]['features']
         wtcost = dt.type(0)
         for L in self.spec:                                                  # layer.py:109-117
@@ -765,7 +829,19 @@ class OracleNet:
         for li in range(len(self.spec) - 1, -1, -1):
             L, c = self.spec[li], caches[li]
             kind = L['kind']
-            if kind in OUT_LAYERS:
+            if kind == 'SoftAuxLayer':
+                P = L['params']
+                W, w2, cw = P[0], P[4], P[6]
+                gz2 = act_backward('relu01', c['z2'], c['aux'], g @ cw.T)
+                gz1 = act_backward('relu50', c['z1'], c['hid'], gz2 @ w2.T)
+                grads[li] = [c['x'].T @ g, g.sum(axis=0),
+                             c['loc'].T @ gz1, gz1.sum(axis=0), c['hid'].T @ gz2, gz2.sum(axis=0),
+                             c['aux'].T @ g, g.sum(axis=0)]
+                g = (g @ W.T).reshape(c['in_shape']) if li > first_weighted else None
+            elif kind == 'AuxConcatLayer':
+                if g is not None:
+                    g = np.ascontiguousarray(g[:, :L['n_in']]).reshape(c['in_shape'])
+            elif kind in OUT_LAYERS:
                 W, b = L['params']
                 grads[li] = [c['x'].T @ g, g.sum(axis=0)]
                 g = (g @ W.T).reshape(c['in_shape']) if li > first_weighted else None
@@ -822,10 +898,10 @@ class OracleNet:
                 L['params'][k], L['vel'][k] = sgd_update(th, L['vel'][k], gk, reg, self.cur_learn_rate)
 
     # -- test twin (neuralnet.py:257-296, outlayers.py:66-80) ---------------------------------------
-    def test_step(self, x, y):
+    def test_step(self, x, y, aux=None):
         """(mean(pred != y), mean(probs[y]), logprob, y_preds): sym_and_oth_err_rate for the
         non-LOGIT kinds; probs are the raw scores for HingeLayer (outlayers.py:138)."""
-        logprob, caches = self._forward(x, False, 0, 0)
+        logprob, caches = self._forward(x, False, 0, 0, None, aux)
         y = np.asarray(y, np.int64)
         B = logprob.shape[0]
         probs = caches[-1]['probs']

@@ -103,6 +103,33 @@ CASES.update({
         ],
         tp={'SEED': 21, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .4, 'EPOCHS_TO_HALF_RATE': 2},
         channels=2, classes=3, batches=2, steps=5, bump_epoch_at=2),
+    # auxiliary inputs (auxiliary.py): features of a (2,2) side input appended to the hidden
+    # layer's output (never trained: AuxConcatLayer has no reg) ...
+    'auxcat': dict(
+        layers=[
+            ('InputLayer', {'img_sz': 8, 'num_maps': 1}),
+            ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'actvn': 'relu20',
+                           'reg': {'momentum': .6}}),
+            ('PoolLayer', {'pool_sz': 2}),
+            ('HiddenLayer', {'n_out': 12, 'pdrop': .25, 'actvn': 'tanh', 'reg': {'momentum': .6}}),
+            ('AuxConcatLayer', {'n_aux': (5, 9), 'aux_type': 'LocationInfo', 'boost': 2}),
+            ('SoftmaxLayer', {'n_out': 4, 'reg': {'momentum': .6}}),
+        ],
+        tp={'SEED': 31, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .3, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=1, classes=4, batches=2, steps=5, bump_epoch_at=2),
+    # ... or entering the scores of the softmax layer through a trained cross term
+    'softaux': dict(
+        layers=[
+            ('InputLayer', {'img_sz': 8, 'num_maps': 1}),
+            ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'actvn': 'relu20',
+                           'reg': {'momentum': .6}}),
+            ('PoolLayer', {'pool_sz': 2}),
+            ('HiddenLayer', {'n_out': 12, 'actvn': 'tanh', 'reg': {'momentum': .6}}),
+            ('SoftAuxLayer', {'n_out': 4, 'n_aux': (5, 9), 'aux_type': 'LocationInfo',
+                              'reg': {'momentum': .6, 'L2': 1e-3, 'maxnorm': 2.}}),
+        ],
+        tp={'SEED': 32, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .3, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=1, classes=4, batches=2, steps=5, bump_epoch_at=2),
     # ColorLayer as the input layer ...
     'color0': dict(
         layers=[
@@ -165,6 +192,15 @@ def case_data(name):
     return x.astype(np.float32), y
 
 
+def case_aux(name):
+    """Auxiliary corpus (n, 2, 2) for the nets that take one (auxiliary.py:22), else None."""
+    c = CASES[name]
+    if not any(k in ('AuxConcatLayer', 'SoftAuxLayer') for k, _ in c['layers']):
+        return None
+    n = c['tp']['BATCH_SZ'] * c['batches']
+    return np.random.RandomState(99 + sum(map(ord, name))).rand(n, 2, 2).astype(np.float32)
+
+
 def draw_keys(layers):
     """[(stream index, serial, layer index, oracle key)] in the order the reference constructs its
     RandomStreams and draws from them (inlayers.py:72-141, dropout.py:9-13, hidden.py:32-33)."""
@@ -187,6 +223,9 @@ def draw_keys(layers):
         elif kind in ('DropOutLayer', 'HiddenLayer') and a.get('pdrop', 0):
             out.append((stream, 0, li, 'mask'))
             stream += 1
+        elif kind in ('AuxConcatLayer', 'SoftAuxLayer'):     # LocationInfo's mix (auxiliary.py:25-27)
+            out.append((stream, 0, li, 'auxu'))
+            stream += 1
         elif kind == 'ColorLayer' and not (a.get('gamma', 1) == 1 and a.get('balance', 1) == 1):
             for k in range(3):                      # pos_rand: balance, gamma, gamma (color.py:36-42)
                 out.append((stream, k, li, 'color%d' % k))
@@ -201,6 +240,8 @@ def rand_table(g, layers, prefix):
         v = g['%s_%d_%s' % (prefix, li, key)]
         if key.startswith('color'):
             col.setdefault(li, [None] * 3)[int(key[-1])] = v
+        elif key == 'auxu':
+            rand[(li, 'auxu')] = v
         elif key in ('flip', 'mask'):
             shape = tuple(g['%s_%d_%s_shape' % (prefix, li, key)])
             rand[(li, key)] = np.unpackbits(v)[:int(np.prod(shape))].reshape(shape).astype(np.float32)
@@ -287,8 +328,13 @@ def generate(name, write=True):
             k += 1
     xs = theano.shared(x, borrow=True)
     ys = tt.cast(theano.shared(y, borrow=True), 'int32')           # train.py:27-31 share()
-    train = net.get_trin_model(xs, ys)
-    test = net.get_test_model(xs, ys)
+    aux = case_aux(name)
+    auxs = None
+    if aux is not None:
+        rec['aux'] = aux
+        auxs = theano.shared(aux, borrow=True)
+    train = net.get_trin_model(xs, ys, auxs)
+    test = net.get_test_model(xs, ys, auxs)
     for s in range(c['steps']):
         if s == c['bump_epoch_at']:
             net.inc_epoch_set_rate()
@@ -299,9 +345,11 @@ def generate(name, write=True):
         store_draws(rec, 's%d' % s, train.draws, c['layers'], base)
     k = 0
     for lyr in net.tr_layers:
-        for p, acc in zip(lyr.params, getattr(lyr, 'accumulated_updates', [])):
+        accs = getattr(lyr, 'accumulated_updates', [])           # none for layers without reg
+        for j, p in enumerate(lyr.params):
             rec['w_%d' % k], rec['wd_%d' % k] = thin(p.get_value()), digest(p.get_value())
-            rec['v_%d' % k], rec['vd_%d' % k] = thin(acc.get_value()), digest(acc.get_value())
+            if j < len(accs):
+                rec['v_%d' % k], rec['vd_%d' % k] = thin(accs[j].get_value()), digest(accs[j].get_value())
             k += 1
     rec['n_params'] = np.int64(k)
     for b in range(c['batches']):

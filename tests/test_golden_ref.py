@@ -83,12 +83,17 @@ def test_training_steps_match_the_reference_graph(name):
     x, y = g['x'], g['y']
     xc, yc = MR.case_data(name)
     assert np.array_equal(x, xc) and np.array_equal(y, yc)
+    aux = g['aux'] if 'aux' in g.files else None
+
+    def auxb(b):
+        return None if aux is None else aux[b * B:(b + 1) * B]
     for s in range(c['steps']):
         if s == c['bump_epoch_at']:
             on.inc_epoch_set_rate()                                   # neuralnet.py:310-312
         b = s % c['batches']
         rand = MR.rand_table(g, c['layers'], 's%d' % s)
-        cost, lp = on.train_step(x[b * B:(b + 1) * B], y[b * B:(b + 1) * B], step=s, rand=rand)
+        cost, lp = on.train_step(x[b * B:(b + 1) * B], y[b * B:(b + 1) * B], step=s, rand=rand,
+                                 aux=auxb(b))
         assert abs(cost - g['cost_%d' % s]) <= TOL_STEP * abs(g['cost_%d' % s]), 'cost, step %d' % s
         assert rel(lp, g['logprob_%d' % s]) < TOL_STEP, 'logprob, step %d' % s
         assert rel(on.last_features, g['feat_%d' % s]) < TOL_STEP, 'features, step %d' % s
@@ -96,11 +101,12 @@ def test_training_steps_match_the_reference_graph(name):
     for L in on.spec:
         for j, t in enumerate(L['params'] or []):
             check_tensor(t, g['w_%d' % k], g['wd_%d' % k], TOL_WTS, 'weights %d' % k)
-            check_tensor(L['vel'][j], g['v_%d' % k], g['vd_%d' % k], TOL_WTS, 'momentum %d' % k)
+            if 'v_%d' % k in g.files:          # layers without reg have no momentum buffers
+                check_tensor(L['vel'][j], g['v_%d' % k], g['vd_%d' % k], TOL_WTS, 'momentum %d' % k)
             k += 1
     assert k == int(g['n_params'])
     for b in range(c['batches']):                                     # neuralnet.py:257-277
-        err, py, _, _ = on.test_step(x[b * B:(b + 1) * B], y[b * B:(b + 1) * B])
+        err, py, _, _ = on.test_step(x[b * B:(b + 1) * B], y[b * B:(b + 1) * B], aux=auxb(b))
         assert abs(err - g['test_%d' % b][0]) < 1e-6
         assert abs(py - g['test_%d' % b][1]) < TOL_WTS
 
@@ -179,7 +185,9 @@ def test_gpu_training_matches_the_reference_graph(name):
     from theanet_b200.neuralnet import NeuralNet
     c, g, on = load(name)
     net = NeuralNet(copy.deepcopy(c['layers']), copy.deepcopy(c['tp']))
-    fn = net.get_trin_model(g['x'], g['y'])
+    aux = g['aux'] if 'aux' in g.files else None
+    assert net.takes_aux() == (aux is not None)
+    fn = net.get_trin_model(g['x'], g['y'], aux)
     for s in range(c['steps']):
         if s == c['bump_epoch_at']:
             net.inc_epoch_set_rate()
@@ -200,12 +208,13 @@ def test_gpu_training_matches_the_reference_graph(name):
             # accumulated momentum, so they inherit its tolerance
             tol_w = tol_v if t.ndim == 1 else TOL_GPU
             assert rel(MR.thin(t), g['w_%d' % k]) < tol_w, 'weights %d' % k
-            assert rel(MR.thin(vel[li][j]), g['v_%d' % k]) < tol_v, 'momentum %d' % k
+            if 'v_%d' % k in g.files:
+                assert rel(MR.thin(vel[li][j]), g['v_%d' % k]) < tol_v, 'momentum %d' % k
             got, want = MR.digest(t), g['wd_%d' % k]
             assert abs(got[1] - want[1]) <= 4 * tol_w * want[1] + 1e-30
             k += 1
     assert k == int(g['n_params'])
-    test = net.get_test_model(g['x'], g['y'])
+    test = net.get_test_model(g['x'], g['y'], aux)
     for b in range(c['batches']):
         err, py = test(b)[:2]
         assert abs(err - g['test_%d' % b][0]) < 1e-6

@@ -745,3 +745,39 @@ def test_color_jitter(C, B, Cm, S, balance, gamma, maxval):
     C.call('tn_color_jitter', C.ptr(xd), C.ptr(xd), B, Cm, S, lb, lg, maxval, 0, None, C.ptr(dev(u2)), None)
     sync()                                                         # in place, injected draws
     assert rel(xd.cpu().numpy(), O.color_jitter(x, prm, u2)) < 1e-5
+
+
+def test_aux_location_mix_and_column_plumbing(C):
+    """auxiliary.py:25-33,80: LocationInfo's input mix on its Philox stream / injected / test
+    mean, and the concat / slice / add kernels around it."""
+    rng = np.random.default_rng(5)
+    B, seed, step, s0 = 37, 77, 4, 20
+    aux = rng.random((B, 2, 2)).astype(np.float32)
+    ctl = make_ctl(C, step=step, sample0=s0)
+    ad = dev(aux.reshape(B, 4))
+    loc = torch.zeros((B, 2), device='cuda')
+    u = philox.aux_uniforms(seed, step, np.arange(s0, s0 + B)).reshape(B, 1)
+    want = (aux[:, 0, :] * u + aux[:, 1, :] * (np.float32(1) - u)) * np.float32(1.5)
+    C.call('tn_aux_location_mix', C.ptr(ad), C.ptr(loc), B, 1.5, 1, seed, C.ptr(ctl), None, None)
+    sync()
+    assert np.array_equal(loc.cpu().numpy(), want.astype(np.float32))
+    u2 = rng.random(B).astype(np.float32)
+    C.call('tn_aux_location_mix', C.ptr(ad), C.ptr(loc), B, 1.0, 1, 0, None, C.ptr(dev(u2)), None)
+    sync()
+    assert np.array_equal(loc.cpu().numpy(), aux[:, 0, :] * u2[:, None] + aux[:, 1, :] * (np.float32(1) - u2[:, None]))
+    C.call('tn_aux_location_mix', C.ptr(ad), C.ptr(loc), B, 2.0, 0, 0, None, None, None)
+    sync()
+    assert np.array_equal(loc.cpu().numpy(), (aux[:, 0, :] + aux[:, 1, :]) / np.float32(2) * np.float32(2))
+    a, c = rng.standard_normal((B, 12)).astype(np.float32), rng.standard_normal((B, 9)).astype(np.float32)
+    out = torch.zeros((B, 21), device='cuda')
+    C.call('tn_concat_cols', C.ptr(dev(a)), 12, C.ptr(dev(c)), 9, C.ptr(out), B, None)
+    sync()
+    assert np.array_equal(out.cpu().numpy(), np.concatenate([a, c], axis=1))
+    back = torch.zeros((B, 9), device='cuda')
+    C.call('tn_slice_cols', C.ptr(out), 21, 12, 9, C.ptr(back), B, None)
+    sync()
+    assert np.array_equal(back.cpu().numpy(), c)
+    d1, d2 = dev(a.copy()), dev(a[::-1].copy())
+    C.call('tn_add_inplace', C.ptr(d1), C.ptr(d2), a.size, None)
+    sync()
+    assert np.array_equal(d1.cpu().numpy(), a + a[::-1])

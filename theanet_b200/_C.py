@@ -80,6 +80,10 @@ SIGNATURES = {
     'tn_meanpool_fwd': (_I, [_P, _P, _I, _I, _P]),
     'tn_meanpool_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'tn_color_jitter': (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _U64, _P, _P, _P]),
+    'tn_aux_location_mix': (_I, [_P, _P, _I, _F, _I, _U64, _P, _P, _P]),
+    'tn_concat_cols': (_I, [_P, _I, _P, _I, _P, _I, _P]),
+    'tn_slice_cols': (_I, [_P, _I, _I, _I, _P, _I, _P]),
+    'tn_add_inplace': (_I, [_P, _P, _I64, _P]),
     'tn_dropout_apply': (_I, [_P, _P, _I, _I, _D, _U64, _P, _P, _F, _P]),
     'tn_act_bwd': (_I, [_P, _P, _P, _I64, _I, _I, _P]),
     'tn_softmax_nll_fwd_bwd': (_I, [_P, _P, _P, _P, _I, _I, _F, _P, _P, _P, _P]),

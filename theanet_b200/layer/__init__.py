@@ -6,3 +6,4 @@ from .convpool import ConvLayer, PoolLayer, MeanLayer
 from .dropout import DropOutLayer
 from .hidden import HiddenLayer
 from .outlayers import SoftmaxLayer, ExpLossLayer, HingeLayer, OutputLayer, OUT_KINDS
+from .auxiliary import SoftAuxLayer, AuxConcatLayer, LocationInfo

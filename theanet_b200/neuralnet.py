@@ -28,7 +28,7 @@ from . import layer
 from .dist import DistContext
 from .layer import (InputLayer, ElasticLayer, ColorLayer, ConvLayer, PoolLayer, MeanLayer,
                     DropOutLayer, HiddenLayer, SoftmaxLayer, ExpLossLayer, HingeLayer, OutputLayer,
-                    OUT_KINDS)
+                    AuxConcatLayer, SoftAuxLayer, OUT_KINDS)
 
 # ########################### Helper Functions #################################
 
@@ -123,6 +123,15 @@ class NeuralNet():
         while self.num_layers < len(layers):
             self.append_next_layer()
         assert isinstance(self.tr_layers[-1], OutputLayer), "last layer must be an output layer"
+        # Handle Auxiliary input (neuralnet.py:99-104)
+        self.aux_index = None
+        for li, tr_layer in enumerate(self.tr_layers):
+            if type(tr_layer) in (AuxConcatLayer, SoftAuxLayer):
+                assert self.aux_index is None, "Multiple Aux Inputs"
+                self.aux_index = li
+                self.aux_inpt_tr = tr_layer.aux_inpt
+                self.aux_inpt_te = self.te_layers[li].aux_inpt
+        self._aux_corpus = None
 
         if 'CUR_EPOCH' not in training_params:
             training_params['CUR_EPOCH'] = 0
@@ -165,7 +174,8 @@ class NeuralNet():
                                    **layer_args)
         elif curr_layer_type is DropOutLayer:
             curr_layer = DropOutLayer(tr_inpt, self.rand_gen, prev_tr_layer.n_out, **layer_args)
-        elif curr_layer_type in (HiddenLayer, SoftmaxLayer, ExpLossLayer, HingeLayer):
+        elif curr_layer_type in (AuxConcatLayer, HiddenLayer, SoftmaxLayer, SoftAuxLayer,
+                                 ExpLossLayer, HingeLayer):
             te_inpt = te_inpt.flatten(2)
             curr_layer = curr_layer_type(tr_inpt.flatten(2), wts, self.rand_gen,
                                          prev_tr_layer.n_out, **layer_args)
@@ -328,8 +338,18 @@ class NeuralNet():
                     nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
                         B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
                 self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
+        # auxiliary-input scratch (auxiliary.py): the gathered (B,2,2) rows, the mixed input, the
+        # two LocationInfo activations and, for SoftAuxLayer, their gradients and the cross term
+        if self.aux_index is not None:
+            ai = self.tr_layers[self.aux_index].aux_info
+            z = lambda *shp: torch.zeros(shp, dtype=f32, device=dev)   # noqa: E731
+            self.aux_batch, self.aux_loc = z(B, 4), z(B, 2)
+            self.aux_hid, self.aux_out = z(B, ai.n_hid), z(B, ai.n_out)
+            self.aux_ghid, self.aux_gout = z(B, ai.n_hid), z(B, ai.n_out)
+            self.aux_cross = z(B, n_out)
         # classifier head (narrow SoftmaxLayer) on the fused kernels of head.cu
         self.head = bool(self.fuse_head and self.trainable[-1] and self.plain_nll and
+                         not isinstance(last, SoftAuxLayer) and
                          _C.lib.tn_softmax_head_supported(last.n_in, last.n_out))
         if self.head:
             nb = _C.lib.tn_softmax_head_workspace_bytes(B, last.n_in, last.n_out)
@@ -550,14 +570,60 @@ class NeuralNet():
                 else:
                     _C.call('tn_dropout_apply', _C.ptr(x), _C.ptr(out), B, n, 1.0, 0, ctl, None,
                             float(lyr.test_scale), st)
-            elif isinstance(lyr, HiddenLayer):        # incl. SoftmaxLayer (scores only)
+            elif isinstance(lyr, AuxConcatLayer):     # auxiliary.py:80
+                self._aux_forward(li, lyr.aux_info, train, idxp, st)
+                _C.call('tn_concat_cols', _C.ptr(x), lyr.n_in, _C.ptr(self.aux_out),
+                        lyr.aux_info.n_out, _C.ptr(out), B, st)
+            elif isinstance(lyr, HiddenLayer):        # incl. the output layers (scores only)
                 pkeep = 1. - lyr.pdrop if (train and lyr.pdrop) else 1.0
                 _C.call('tn_dense_fwd', _C.ptr(x), _C.ptr(lyr.w.tensor), _C.ptr(lyr.b.tensor),
                         _C.ptr(out), B, lyr.n_in, lyr.n_out, lyr.act.code, lyr.act.nn, pkeep,
                         lyr.seed or 0, ctl, self._inj(li, 'mask') if train else None,
                         float(lyr.test_scale), st)
+                if isinstance(lyr, SoftAuxLayer):     # + cross_b + aux . cross_w (auxiliary.py:133-134)
+                    ai = lyr.aux_info
+                    self._aux_forward(li, ai, train, idxp, st)
+                    _C.call('tn_dense_fwd', _C.ptr(self.aux_out), _C.ptr(lyr.cross_w.tensor),
+                            _C.ptr(lyr.cross_b.tensor), _C.ptr(self.aux_cross), B, ai.n_out,
+                            lyr.n_out, _C.ACT_LINEAR, 0, 1.0, 0, ctl, None, 1.0, st)
+                    _C.call('tn_add_inplace', _C.ptr(out), _C.ptr(self.aux_cross),
+                            B * lyr.n_out, st)
             else:
                 raise NotImplementedError(type(lyr).__name__)
+
+    def _aux_forward(self, li, ai, train, idxp, st):
+        """LocationInfo (auxiliary.py:14-57): gather this batch's (2,2) rows, mix them, two small
+        dense layers -> self.aux_out."""
+        B, ctl = self.local_bsz, _C.ptr(self.ctl)
+        assert self._aux_corpus is not None, "Auxillary data not supplied"
+        _C.call('tn_elastic_warp', _C.ptr(self._aux_corpus), idxp, ctl, B, 1, 2, 0, 0, None, None,
+                0.0, None, 0, _C.ptr(self.aux_batch), st)              # row gather, 4 floats each
+        _C.call('tn_aux_location_mix', _C.ptr(self.aux_batch), _C.ptr(self.aux_loc), B,
+                float(ai.boost), int(train), ai.seed or 0, ctl,
+                self._inj(li, 'auxu') if train else None, st)
+        _C.call('tn_dense_fwd', _C.ptr(self.aux_loc), _C.ptr(ai.w1.tensor), _C.ptr(ai.b1.tensor),
+                _C.ptr(self.aux_hid), B, 2, ai.n_hid, ai.act1.code, ai.act1.nn, 1.0, 0, ctl, None,
+                1.0, st)
+        _C.call('tn_dense_fwd', _C.ptr(self.aux_hid), _C.ptr(ai.w2.tensor), _C.ptr(ai.b2.tensor),
+                _C.ptr(self.aux_out), B, ai.n_hid, ai.n_out, ai.act2.code, ai.act2.nn, 1.0, 0, ctl,
+                None, 1.0, st)
+
+    def _aux_backward(self, lyr, g, st):
+        """SoftAuxLayer's extra parameters (auxiliary.py:108-141): the cross term and, through
+        it, the two LocationInfo layers.  g = dL/d(scores)."""
+        B, ctl, ai = self.local_bsz, _C.ptr(self.ctl), lyr.aux_info
+        _C.call('tn_dense_bwd_weights', _C.ptr(self.aux_out), _C.ptr(g), _C.ptr(lyr.cross_w.grad),
+                _C.ptr(lyr.cross_b.grad), B, ai.n_out, lyr.n_out, st)
+        _C.call('tn_dense_bwd_data', _C.ptr(g), _C.ptr(lyr.cross_w.tensor), _C.ptr(self.aux_gout),
+                B, ai.n_out, lyr.n_out, _C.ptr(self.aux_out), ai.act2.code, ai.act2.nn, 1.0, 0, ctl,
+                None, st)
+        _C.call('tn_dense_bwd_weights', _C.ptr(self.aux_hid), _C.ptr(self.aux_gout),
+                _C.ptr(ai.w2.grad), _C.ptr(ai.b2.grad), B, ai.n_hid, ai.n_out, st)
+        _C.call('tn_dense_bwd_data', _C.ptr(self.aux_gout), _C.ptr(ai.w2.tensor),
+                _C.ptr(self.aux_ghid), B, ai.n_hid, ai.n_out, _C.ptr(self.aux_hid), ai.act1.code,
+                ai.act1.nn, 1.0, 0, ctl, None, st)
+        _C.call('tn_dense_bwd_weights', _C.ptr(self.aux_loc), _C.ptr(self.aux_ghid),
+                _C.ptr(ai.w1.grad), _C.ptr(ai.b1.grad), B, 2, ai.n_hid, st)
 
     def _prefetching(self):
         return (self.field_prefetch and self.use_graph and not self.inject
@@ -628,7 +694,19 @@ class NeuralNet():
                     _C.call('tn_softmax_head_bwd_weights', _C.ptr(x), _C.ptr(g),
                             _C.ptr(lyr.w.grad), _C.ptr(lyr.b.grad), _C.ptr(self.ws_head), B,
                             lyr.n_in, lyr.n_out, _C.ptr(self.rowloss), _C.ptr(self.nll_sum), sw)
+            elif isinstance(lyr, AuxConcatLayer):
+                if below:          # gradient of the concatenation wrt its first n_in columns
+                    _C.call('tn_slice_cols', _C.ptr(g), lyr.n_out, 0, lyr.n_in, _C.ptr(dx), B, st)
+                    if fuse:
+                        po, ac, nn, pkp, sd, mi = fuse
+                        if pkp < 1.0 or mi is not None:
+                            _C.call('tn_dropout_apply', _C.ptr(dx), _C.ptr(dx), B, lyr.n_in, pkp, sd,
+                                    ctl, mi, 1.0, st)
+                        _C.call('tn_act_bwd', _C.ptr(dx), _C.ptr(po), _C.ptr(dx), B * lyr.n_in, ac,
+                                nn, st)
             elif isinstance(lyr, HiddenLayer):
+                if self.trainable[li] and isinstance(lyr, SoftAuxLayer):
+                    self._aux_backward(lyr, g, st)
                 if self.trainable[li]:
                     with self._wgrad_stream() as sw:
                         _C.call('tn_dense_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
@@ -899,6 +977,19 @@ class NeuralNet():
         yb = torch.empty(B, dtype=torch.int32, device=self.device)
         return xb, yb, (x, y)
 
+    def _stage_aux(self, aux_data, resident):
+        """The auxiliary corpus (N, 2, 2) -> device (N, 4); None when the net takes none."""
+        if self.aux_index is None:
+            return None
+        assert aux_data is not None, "Auxillary data not supplied"       # neuralnet.py:216,267
+        assert resident, "auxiliary inputs need the HBM-resident corpus (resident=True)"
+        a = _as_numpy(aux_data)
+        if isinstance(a, torch.Tensor):
+            a = a.to(torch.float32).reshape(-1, 4).contiguous()
+        else:
+            a = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 4))
+        return a.to(self.device)
+
     # ------------------------------------------------------------------------------------------
     # public API (theanet/neuralnet.py:203-296)
     # ------------------------------------------------------------------------------------------
@@ -911,8 +1002,8 @@ class NeuralNet():
         variable); resident=False leaves it in pinned host memory and copies each minibatch
         host->device inside the call.  lazy=True returns device tensors without synchronising.
         """
-        assert aux_data is None, "auxiliary inputs are out of scope"
         xd, yd, host = self._stage(x_data, y_data, resident)
+        auxd = self._stage_aux(aux_data, resident)
         B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
         key = ('train', id(xd), take_index_list)
         h_cost = torch.zeros(1, dtype=torch.float32, pin_memory=self.device.type == 'cuda')
@@ -955,6 +1046,7 @@ class NeuralNet():
             bufs = None
 
         def training_fn(indx):
+            self._aux_corpus = auxd
             if bufs is not None:
                 if pre['index'] == int(indx):
                     slot = pre['slot']
@@ -1006,12 +1098,13 @@ class NeuralNet():
 
     def get_test_model(self, x_data, y_data, aux_data=None, preds_feats=False, resident=True):
         """``f(batch_index) -> (sym_err_rate, mean p[y]) [+ (features, y_preds)]``."""
-        assert aux_data is None, "auxiliary inputs are out of scope"
         xd, yd, host = self._stage(x_data, y_data, resident)
+        auxd = self._stage_aux(aux_data, resident)
         B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
         key = ('test', id(xd))
 
         def test_fn(indx):
+            self._aux_corpus = auxd
             lo = int(indx) * B + rank * Bl
             if host is None:
                 row0 = lo
@@ -1030,7 +1123,7 @@ class NeuralNet():
         return test_fn
 
     def takes_aux(self):
-        return False
+        return self.aux_index is not None
 
     def get_data_test_model(self, get_output_of_layers=()):
         """``f(x_batch) -> [features, y_preds, *layer outputs]`` on raw input batches of exactly
@@ -1038,9 +1131,10 @@ class NeuralNet():
         Bl = self.local_bsz
         yd = torch.zeros(Bl, dtype=torch.int32, device=self.device)
 
-        def data_test_fn(x):
+        def data_test_fn(x, aux=None):
             xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
             assert xd.shape[0] == Bl, "expected a batch of {} images".format(Bl)
+            self._aux_corpus = self._stage_aux(aux, True)      # inputs += [aux] (neuralnet.py:288-290)
             self._set_ctl(0)
             self._test_launches(xd.reshape((Bl,) + self.tr_layers[0].output.shape), None, yd)
             outs = [self.feat.cpu().numpy(), self.preds.cpu().numpy()]

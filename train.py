@@ -127,10 +127,13 @@ def main(argv):
     # permutation of the training set every epoch and feeds index lists (neuralnet.py:228-234);
     # the default walks the batches in their fixed order like the reference (train.py:210)
     shuffle = bool(tr_prms.get('SHUFFLE', False))
-    training_fn = net.get_trin_model(trin_x, data.training_y, take_index_list=shuffle)
+    # auxiliary inputs when the net wants them and the dataset has them (reference train.py:131-135)
+    trin_aux = getattr(data, 'training_aux', None) if net.takes_aux() else None
+    test_aux = getattr(data, 'testing_aux', None) if net.takes_aux() else None
+    training_fn = net.get_trin_model(trin_x, data.training_y, trin_aux, take_index_list=shuffle)
     order_rng = np.random.RandomState(tr_prms['SEED'] + 1)
-    test_fn_tr = net.get_test_model(trin_x, data.training_y)
-    test_fn_te = net.get_test_model(test_x, data.testing_y)
+    test_fn_tr = net.get_test_model(trin_x, data.training_y, trin_aux)
+    test_fn_te = net.get_test_model(test_x, data.testing_y, test_aux)
 
     B, n_epochs = tr_prms['BATCH_SZ'], tr_prms['NUM_EPOCHS']
     aux_name = 'BitErr' if net.tr_layers[-1].kind == 'LOGIT' else 'P(MLE)'
