@@ -124,6 +124,14 @@ size_t tn_conv2d_wgrad_workspace_bytes(int B, int C, int S, int M, int f);
 int tn_conv2d_wgrad(const float *x, const float *gz, float *dW, float *db, void *workspace, int B,
                     int C, int S, int M, int f, int pad_lo, int out_sz, void *stream);
 
+/* ---- strided ConvLayer (convpool.py:54-56,69-70): nnet.conv2d(subsample=(s,s)) is the stride-1
+ * convolution sampled on the lattice (i*s, j*s).  out[p,i,j] = x[p,i*s,j*s]; the gradient puts
+ * g[p,i,j] back on the lattice and zeros elsewhere, after which the stride-1 wgrad / dgrad apply. */
+int tn_subsample2d(const float *x, float *out, int planes, int S, int stride, int out_sz,
+                   void *stream);
+int tn_upsample2d_zero(const float *g, float *out, int planes, int S, int stride, int out_sz,
+                       void *stream);
+
 /* ---- MeanLayer (theanet/layer/convpool.py:129-144): out[plane] = mean over the S x S map --------- */
 int tn_meanpool_fwd(const float *x, float *out, int planes, int S, void *stream);
 /* dx[plane,i] = dout[plane] / (S*S) * act'(x[plane,i]); x = output of the layer below (NULL or

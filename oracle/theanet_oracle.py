@@ -533,16 +533,21 @@ class OracleNet:
                 L['num_maps'], L['out_sz'] = num_maps, out_sz
             elif name == 'ConvLayer':
                 f, M = args['filter_sz'], args['num_maps']
-                assert args.get('stride', 1) == 1, "only stride 1 (all named configs)"
+                stride = args.get('stride', 1)
                 actvn = args.get('actvn', 'relu50')
                 mode = args.get('mode', 'valid')
+                assert stride == 1 or mode == 'valid', "For Same mode stride should be 1"  # convpool.py:58
                 if wts is None:
                     W, b = init_wb(rand_gen, (M, num_maps, f, f), (M,),
                                    num_maps * f * f, M * f * f, actvn)       # convpool.py:46-50
                 else:
                     W, b = [np.asarray(t, np.float32) for t in wts]
                 _, out_sz = conv_geometry(out_sz, f, mode)
-                L.update(actvn=actvn, mode=mode, in_maps=num_maps)
+                # conv2d(subsample=(s,s)) samples the stride-1 output at (i*s, j*s); the reference
+                # books out_sz // s (convpool.py:70), which is that size only when s divides it
+                assert out_sz % stride == 0, "out_sz is not a multiple of the stride"
+                out_sz //= stride
+                L.update(actvn=actvn, mode=mode, in_maps=num_maps, stride=stride)
                 num_maps = M
                 n_out = M * out_sz ** 2
                 L['params'] = [W.astype(self.dtype), b.astype(self.dtype)]
@@ -712,6 +717,9 @@ class OracleNet:
                     a, W = bf16_round(a).astype(dt), bf16_round(W).astype(dt)
                     c['Wr'] = W
                 z, cc = conv_forward(a, W, L['mode'])
+                if L['stride'] != 1:
+                    c['full_shape'] = z.shape
+                    z = np.ascontiguousarray(z[:, :, ::L['stride'], ::L['stride']])
                 z = z + b[None, :, None, None]
                 c.update(cc=cc, z=z)
                 a = act_forward(L['actvn'], z)
@@ -870,6 +878,10 @@ class OracleNet:
                 gz = act_backward(L['actvn'], c['z'], c['a'], g)
                 if L['tc']:
                     gz, W = bf16_round(gz).astype(dt), c['Wr']
+                if L['stride'] != 1:
+                    gfull = np.zeros(c['full_shape'], gz.dtype)
+                    gfull[:, :, ::L['stride'], ::L['stride']] = gz
+                    gz = gfull
                 dW, db, dx = conv_backward(gz, W, c['cc'], need_dx=li > first_weighted)
                 if L['tc'] and dx is not None:
                     dx = bf16_round(dx).astype(dt)

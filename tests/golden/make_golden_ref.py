@@ -103,6 +103,19 @@ CASES.update({
         ],
         tp={'SEED': 21, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .4, 'EPOCHS_TO_HALF_RATE': 2},
         channels=2, classes=3, batches=2, steps=5, bump_epoch_at=2),
+    # strided convolutions (convpool.py:54-56,69-70): 14 -> (f3, stride 2) 12/2 = 6 -> (f4, stride 3) 3/3 = 1
+    'stride': dict(
+        layers=[
+            ('InputLayer', {'img_sz': 14, 'num_maps': 2}),
+            ('ConvLayer', {'num_maps': 4, 'filter_sz': 3, 'stride': 2, 'actvn': 'relu10',
+                           'reg': {'momentum': .6}}),
+            ('ConvLayer', {'num_maps': 5, 'filter_sz': 4, 'stride': 3, 'actvn': 'tanh',
+                           'reg': {'momentum': .6, 'maxnorm': 1.}}),
+            ('HiddenLayer', {'n_out': 10, 'actvn': 'relu', 'reg': {'momentum': .6}}),
+            ('SoftmaxLayer', {'n_out': 3, 'reg': {'momentum': .6}}),
+        ],
+        tp={'SEED': 41, 'BATCH_SZ': 6, 'INIT_LEARNING_RATE': .3, 'EPOCHS_TO_HALF_RATE': 2},
+        channels=2, classes=3, batches=2, steps=5, bump_epoch_at=2),
     # auxiliary inputs (auxiliary.py): features of a (2,2) side input appended to the hidden
     # layer's output (never trained: AuxConcatLayer has no reg) ...
     'auxcat': dict(

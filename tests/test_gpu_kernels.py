@@ -781,3 +781,22 @@ def test_aux_location_mix_and_column_plumbing(C):
     C.call('tn_add_inplace', C.ptr(d1), C.ptr(d2), a.size, None)
     sync()
     assert np.array_equal(d1.cpu().numpy(), a + a[::-1])
+
+
+@pytest.mark.parametrize('planes,S,s', [(7, 12, 2), (3, 9, 3), (5, 8, 1), (2, 10, 5)])
+def test_subsample_and_its_gradient(C, planes, S, s):
+    """Strided ConvLayer plumbing (convpool.py:54-56): sampling lattice and its zero-filled adjoint."""
+    rng = np.random.default_rng(S * s)
+    O = S // s
+    x = rng.standard_normal((planes, S, S)).astype(np.float32)
+    out = torch.zeros((planes, O, O), device='cuda')
+    C.call('tn_subsample2d', C.ptr(dev(x)), C.ptr(out), planes, S, s, O, None)
+    sync()
+    assert np.array_equal(out.cpu().numpy(), x[:, ::s, ::s][:, :O, :O])
+    g = rng.standard_normal((planes, O, O)).astype(np.float32)
+    up = torch.full((planes, S, S), 3., device='cuda')
+    C.call('tn_upsample2d_zero', C.ptr(dev(g)), C.ptr(up), planes, S, s, O, None)
+    sync()
+    want = np.zeros((planes, S, S), np.float32)
+    want[:, :O * s:s, :O * s:s] = g
+    assert np.array_equal(up.cpu().numpy(), want)

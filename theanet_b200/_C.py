@@ -77,6 +77,8 @@ SIGNATURES = {
     'tn_dense_bwd_data': (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _D, _U64, _P, _P, _P]),
     'tn_dense_bwd_weights': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'tn_set_dense_mode': (_I, [_I]),
+    'tn_subsample2d': (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    'tn_upsample2d_zero': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_meanpool_fwd': (_I, [_P, _P, _I, _I, _P]),
     'tn_meanpool_bwd': (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     'tn_color_jitter': (_I, [_P, _P, _I, _I, _I, _F, _F, _F, _U64, _P, _P, _P]),

@@ -78,9 +78,65 @@ __global__ void meanpool_bwd_kernel(const float *__restrict__ dout, const float 
   }
 }
 
+// ---- strided convolution = stride-1 convolution + subsampling (convpool.py:54-56,69-70) ----------
+// out[p,i,j] = x[p, i*s, j*s]
+__global__ void subsample2d_kernel(const float *__restrict__ x, float *__restrict__ out,
+                                   uint32_t total, int S, int s, int O, FastDiv32 divO) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t r = divO.div(t);
+    const int j = (int)(t - r * O);
+    const uint32_t plane = divO.div(r);
+    const int i = (int)(r - plane * O);
+    out[t] = x[((size_t)plane * S + (size_t)i * s) * S + (size_t)j * s];
+  }
+}
+
+// its gradient: out[p,y,x] = g[p, y/s, x/s] on the sampled lattice, 0 elsewhere
+__global__ void upsample2d_zero_kernel(const float *__restrict__ g, float *__restrict__ out,
+                                       uint32_t total, int S, int s, int O, FastDiv32 divS,
+                                       FastDiv32 divs) {
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const uint32_t r = divS.div(t);
+    const uint32_t xx = t - r * S;
+    const uint32_t plane = divS.div(r);
+    const uint32_t yy = r - plane * S;
+    const uint32_t i = divs.div(yy), j = divs.div(xx);
+    const bool on = i * s == yy && j * s == xx && (int)i < O && (int)j < O;
+    out[t] = on ? g[((size_t)plane * O + i) * O + j] : 0.f;
+  }
+}
+
 }  // namespace tn
 
 using namespace tn;
+
+extern "C" int tn_subsample2d(const float *x, float *out, int planes, int S, int stride,
+                              int out_sz, void *stream) {
+  TN_REQUIRE(x && out, TN_ERR_ARG, "tn_subsample2d: null argument");
+  TN_REQUIRE(planes > 0 && S > 0 && stride > 0 && out_sz > 0 && (out_sz - 1) * stride < S,
+             TN_ERR_SHAPE, "tn_subsample2d: bad shape S=%d stride=%d out=%d", S, stride, out_sz);
+  const int64_t total = (int64_t)planes * out_sz * out_sz;
+  TN_REQUIRE((int64_t)planes * S * S < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_subsample2d: tensor too large");
+  const int blocks = (int)min64(ceil_div64(total, 256), (int64_t)kNumSM * 32);
+  subsample2d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, out, (uint32_t)total, S, stride,
+                                                              out_sz, FastDiv32(out_sz));
+  TN_LAUNCH_CHECK("tn_subsample2d");
+  return TN_OK;
+}
+
+extern "C" int tn_upsample2d_zero(const float *g, float *out, int planes, int S, int stride,
+                                  int out_sz, void *stream) {
+  TN_REQUIRE(g && out, TN_ERR_ARG, "tn_upsample2d_zero: null argument");
+  TN_REQUIRE(planes > 0 && S > 0 && stride > 0 && out_sz > 0 && (out_sz - 1) * stride < S,
+             TN_ERR_SHAPE, "tn_upsample2d_zero: bad shape S=%d stride=%d out=%d", S, stride, out_sz);
+  const int64_t total = (int64_t)planes * S * S;
+  TN_REQUIRE(total < (1ll << 32), TN_ERR_UNSUPPORTED, "tn_upsample2d_zero: tensor too large");
+  const int blocks = (int)min64(ceil_div64(total, 256), (int64_t)kNumSM * 32);
+  upsample2d_zero_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      g, out, (uint32_t)total, S, stride, out_sz, FastDiv32(S), FastDiv32(stride));
+  TN_LAUNCH_CHECK("tn_upsample2d_zero");
+  return TN_OK;
+}
 
 extern "C" int tn_meanpool_fwd(const float *x, float *out, int planes, int S, void *stream) {
   TN_REQUIRE(x && out, TN_ERR_ARG, "tn_meanpool_fwd: null argument");

@@ -6,8 +6,11 @@ from .weights import init_wb
 
 
 class ConvLayer(Layer):
-    """True convolution (filter flipped), stride 1, 'valid' or 'same', bias + activation.
-    mode='full' is rejected: the reference's out_sz for it (in+f+1, convpool.py:64) is wrong."""
+    """True convolution (filter flipped), 'valid' or 'same', bias + activation.  mode='full' is
+    rejected: the reference's out_sz for it (in+f+1, convpool.py:64) is wrong.  stride > 1 runs as
+    the stride-1 convolution sampled every `stride` pixels, in 'valid' mode (the reference asserts
+    stride 1 for 'same', :58) and only where its bookkeeping `out_sz //= stride` (:70) agrees with
+    what conv2d(subsample=...) returns, i.e. when in_sz - filter_sz + 1 divides by stride."""
 
     def __init__(self, inpt, wts, rand_gen, batch_sz, num_prev_maps, in_sz, num_maps, filter_sz,
                  stride, mode='valid', actvn='relu50', reg=()):
@@ -16,8 +19,13 @@ class ConvLayer(Layer):
         if mode == 'full':
             raise NotImplementedError("ConvLayer mode='full' is unsupported (the reference's "
                                       "out_sz for it is inconsistent, convpool.py:64)")
-        if stride != 1:
-            raise NotImplementedError("ConvLayer supports stride 1 only")
+        if mode == 'same':
+            assert stride == 1, "For Same mode stride should be 1"
+        if stride != 1 and (in_sz - filter_sz + 1) % stride:
+            raise NotImplementedError(
+                "ConvLayer stride {}: in_sz - filter_sz + 1 = {} is not a multiple of it, the "
+                "reference's out_sz (convpool.py:70) would disagree with the convolution's".format(
+                    stride, in_sz - filter_sz + 1))
         filter_shape = (num_maps, num_prev_maps, filter_sz, filter_sz)
         fan_in = num_prev_maps * filter_sz * filter_sz
         fan_out = num_maps * filter_sz * filter_sz
@@ -30,6 +38,8 @@ class ConvLayer(Layer):
         else:
             self.pad_lo = 0
             self.out_sz = in_sz - filter_sz + 1
+        self.full_sz = self.out_sz              # output side of the stride-1 convolution
+        self.stride = stride
         self.out_sz //= stride
         self.actvn = actvn
         self.act = activation_by_name(actvn)

@@ -325,6 +325,7 @@ class NeuralNet():
         # fused small-channel kernels (conv_fused.cu)
         self.ws = {}
         self.conv_fused = {}
+        self.conv_full = {}
         self._plan_conv_tc()
         for li, lyr in enumerate(self.tr_layers):
             if isinstance(lyr, ConvLayer) and li in self.conv_tc:
@@ -333,7 +334,12 @@ class NeuralNet():
                 nb = _C.lib.tn_conv2d_wgrad_workspace_bytes(B, lyr.num_prev_maps, lyr.in_sz,
                                                             lyr.num_maps, lyr.filter_sz)
                 nxt = self.tr_layers[li + 1] if li + 1 < len(self.tr_layers) else None
-                if self.fuse_conv and isinstance(nxt, PoolLayer) and self._fused_conv_ok(lyr):
+                if lyr.stride != 1:      # stride-1 activations and gradients at full resolution
+                    full = (B, lyr.num_maps, lyr.full_sz, lyr.full_sz)
+                    self.conv_full[li] = (torch.empty(full, dtype=f32, device=dev),
+                                          torch.empty(full, dtype=f32, device=dev))
+                if (self.fuse_conv and lyr.stride == 1 and isinstance(nxt, PoolLayer)
+                        and self._fused_conv_ok(lyr)):
                     self.conv_fused[li] = nxt
                     nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
                         B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
@@ -378,6 +384,8 @@ class NeuralNet():
         lyr = self.tr_layers[li]
         nxt = self.tr_layers[li + 1] if li + 1 < len(self.tr_layers) else None
         if lyr.mode != 'same' or lyr.act.code not in (_C.ACT_LINEAR, _C.ACT_RELU, _C.ACT_LEAKY):
+            return None
+        if lyr.stride != 1:
             return None
         if isinstance(nxt, MeanLayer):                # float32 path: its backward fuses act' itself
             return None
@@ -550,9 +558,13 @@ class NeuralNet():
                         lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
                         lyr.out_sz, lyr.act.code, lyr.act.nn, pl.pool_sz, pl.out_sz, st)
             elif isinstance(lyr, ConvLayer):
+                dst = self.conv_full[li][0] if lyr.stride != 1 else out
                 _C.call('tn_conv2d_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor), _C.ptr(lyr.b.tensor),
-                        _C.ptr(out), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz,
-                        lyr.pad_lo, lyr.out_sz, lyr.act.code, lyr.act.nn, st)
+                        _C.ptr(dst), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz,
+                        lyr.pad_lo, lyr.full_sz, lyr.act.code, lyr.act.nn, st)
+                if lyr.stride != 1:                   # conv2d(subsample=(s, s)), convpool.py:54-56
+                    _C.call('tn_subsample2d', _C.ptr(dst), _C.ptr(out), B * lyr.num_maps,
+                            lyr.full_sz, lyr.stride, lyr.out_sz, st)
             elif isinstance(lyr, PoolLayer) and ((li - 1) in self.conv_fused or
                                                  ((li - 1) in self.conv_tc and
                                                   self.conv_tc[li - 1].pool is not None)):
@@ -764,16 +776,21 @@ class NeuralNet():
                             _C.ptr(g), _C.ptr(lyr.W.tensor), _C.ptr(dx), _C.ptr(po), *geom, ac, nn,
                             st)
             elif isinstance(lyr, ConvLayer):
+                if lyr.stride != 1:      # dL/dz back on the sampling lattice, zeros elsewhere
+                    gfull = self.conv_full[li][1]
+                    _C.call('tn_upsample2d_zero', _C.ptr(g), _C.ptr(gfull), B * lyr.num_maps,
+                            lyr.full_sz, lyr.stride, lyr.out_sz, st)
+                    g = gfull
                 if self.trainable[li]:
                     with self._wgrad_stream() as sw:
                         _C.call('tn_conv2d_wgrad', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.W.grad),
                                 _C.ptr(lyr.b.grad), _C.ptr(self.ws[li]), B, lyr.num_prev_maps,
-                                lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo, lyr.out_sz, sw)
+                                lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo, lyr.full_sz, sw)
                 if below:
                     po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, 0, 0)
                     _C.call('tn_conv2d_dgrad', _C.ptr(g), _C.ptr(lyr.W.tensor), _C.ptr(dx),
                             _C.ptr(po), B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps,
-                            lyr.filter_sz, lyr.pad_lo, lyr.out_sz, ac, nn, st)
+                            lyr.filter_sz, lyr.pad_lo, lyr.full_sz, ac, nn, st)
                     if fuse and fuse[3] < 1.0:
                         raise NotImplementedError("dropout-masked dense output feeding a conv")
             elif isinstance(lyr, PoolLayer) and ((li - 1) in self.conv_fused or
