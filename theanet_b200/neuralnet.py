@@ -12,6 +12,10 @@ optimiser launch) that is captured once into a CUDA graph and replayed per minib
 scalars (step counter, corpus row, learning rate) live in a small device control block that the
 graph refreshes from pinned host memory.
 
+Beyond the hot path the same engine runs ColorLayer, MeanLayer, strided
+convolutions, the auxiliary-input layers, ExpLossLayer, HingeLayer and the nllsq / truncated-NLL
+losses; CenteredOutLayer is not implemented (it cannot be trained in the reference either).
+
 PyTorch is used for device memory, streams, CUDA graphs and torch.distributed only.
 """
 import ctypes
