@@ -13,7 +13,6 @@ minibatch and a device->host read of cost + log-probabilities.
 """
 import argparse
 import ast
-import copy
 import json
 import os
 import subprocess
