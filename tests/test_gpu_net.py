@@ -118,6 +118,18 @@ def test_mnist_prms_training_matches_oracle(B, use_graph):
     run_pair(prms, x, y, 10, use_graph)
 
 
+def test_mnist_prms_at_the_bench_batch_size():
+    """BASELINE configs[1] exactly as bench.py runs it -- 1024 images per step, CUDA graph, tcgen05
+    3xTF32 dense layers, fused conv+pool and classifier-head kernels, elastic-field prefetch --
+    against the oracle for three steps (the sharding property at this size, gradient of the batch =
+    mean of the shard gradients, is covered by tests/test_gpu_dist.py and tests/test_dist_gloo.py)."""
+    prms = load_prms('mnist.prms', 1024, 28)
+    x, y = synth(2048, 1, 28, 10)
+    net, on, costs = run_pair(prms, x, y, 3, True, check_at=(1, 3))
+    assert net.head and net.conv_fused and net.field_prefetch      # the bench path, not a fallback
+    assert all(np.isfinite(c[0]) for c in costs)
+
+
 def test_mnist_prms_100_steps_curve():
     prms = load_prms('mnist.prms', 20, 28)
     x, y = synth(20 * 10, 1, 28, 10)
