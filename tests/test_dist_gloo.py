@@ -95,3 +95,46 @@ def test_shard_bounds():
     assert shard_bounds(3, 1024, 7, 8) == (3 * 1024 + 7 * 128, 4 * 1024)
     with pytest.raises(AssertionError):
         shard_bounds(0, 10, 0, 4)
+
+
+def _facade_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world))
+    from theanet_b200.dist import init_from_env
+    from theanet_b200.neuralnet import NeuralNet
+    import make_golden as MG
+    ctx = init_from_env('cpu')
+    p = MG.load_prms('mnist.prms', 16, 28)
+    p['training_params']['SEED'] = 100 + rank          # replicas must not depend on the local seed
+    net = NeuralNet(p['layers'], p['training_params'], device='cpu', dist=ctx)
+    net.step_count = 5
+    net._set_ctl(48)
+    from theanet_b200 import _C
+    c = net._ctl_np
+    q.put((rank, net.local_bsz, net.batch_sz, net.theta.numpy().copy(),
+           (int(c[_C.CTL_STEP]), int(c[_C.CTL_SAMPLE0]), int(c[_C.CTL_ROW0])),
+           float(np.float32(net.cur_learn_rate.get_value()))))
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_facade_shards_the_batch_and_starts_from_rank0_weights():
+    """NeuralNet under a 2-rank gloo group on the CPU (construction only -- there is no CPU
+    execution path): BATCH_SZ stays the global minibatch, each rank owns BATCH_SZ / world samples
+    starting at global sample rank * local (what keys the Philox masks), and every replica starts
+    from rank 0's parameters whatever its local SEED drew."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_facade_worker, args=(r, 2, port, q)) for r in range(2)]
+    for pr in procs:
+        pr.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    (r0, l0, b0, th0, ctl0, lr0), (r1, l1, b1, th1, ctl1, lr1) = res
+    assert (l0, b0, l1, b1) == (8, 16, 8, 16)
+    assert np.array_equal(th0, th1) and np.abs(th0).max() > 0
+    assert ctl0 == (5, 0, 48) and ctl1 == (5, 8, 48)
+    assert lr0 == lr1
