@@ -154,3 +154,23 @@ def test_train_driver_helpers():
     assert train.as_images(np.zeros((5, 3, 8, 8))).shape == (5, 3, 8, 8)
     with pytest.raises(ValueError):
         train.as_images(np.zeros((5, 63)))
+
+
+def test_resume_state_carries_every_stream_seed():
+    """get_resume_state / set_resume_state (an extension over the reference's .pkl): momentum
+    buffers, step counter and the seeds of every random stream -- dropout, elastic, colour and the
+    LocationInfo mix -- so that a net rebuilt from `allwts` continues the same streams."""
+    for name in ('softaux', 'mnist', 'color_el'):
+        c = MR.CASES[name]
+        net = nn.NeuralNet(copy.deepcopy(c['layers']), copy.deepcopy(c['tp']), device='cpu')
+        net.step_count = 7
+        st = net.get_resume_state()
+        saved = net.get_init_params()
+        net2 = nn.NeuralNet(saved['layers'], saved['training_params'], saved['allwts'], device='cpu')
+        net2.set_resume_state(st)
+        st2 = net2.get_resume_state()
+        assert st2['seeds'] == st['seeds'] and st2['aux_seeds'] == st['aux_seeds']
+        assert st2['step_count'] == 7
+        assert any(s is not None for s in st['seeds'] + st['aux_seeds'])
+        for a, b in zip(st['velocities'], st2['velocities']):
+            assert all(np.array_equal(u, v) for u, v in zip(a, b))

@@ -1176,8 +1176,9 @@ class NeuralNet():
         key the Philox draws.  ``set_resume_state`` on a net built from the same .pkl continues the
         run bit for bit; a .pkl without it resumes like the reference does (fresh momentum, new
         random streams)."""
+        aux = [getattr(getattr(l, 'aux_info', None), 'seed', None) for l in self.tr_layers]
         return {"velocities": self.get_velocities(), "step_count": int(self.step_count),
-                "seeds": [getattr(l, 'seed', None) for l in self.tr_layers]}
+                "seeds": [getattr(l, 'seed', None) for l in self.tr_layers], "aux_seeds": aux}
 
     def set_resume_state(self, state):
         assert len(state["velocities"]) == len(self.tr_layers) == len(state["seeds"])
@@ -1187,6 +1188,9 @@ class NeuralNet():
                 p.vel.copy_(torch.as_tensor(np.asarray(v, np.float32)).reshape(p.vel.shape))
             if seed is not None:
                 lyr.seed = seed
+        for lyr, seed in zip(self.tr_layers, state.get("aux_seeds", ())):
+            if seed is not None:
+                lyr.aux_info.seed = seed
         self.step_count = int(state["step_count"])
         self._field_step = None
         self._graphs = {}            # captured graphs bake the seeds in as kernel arguments
