@@ -338,3 +338,78 @@ def test_bf16_conv_stack_mode_changes_only_eligible_layers():
     assert np.isfinite(cost) and lp.shape == (2, 10)
     a = on2._forward(x, False, 0, 0)[1][1]['a']     # conv 1 activations are bf16 values
     assert np.array_equal(O.bf16_round(a), a)
+
+
+@pytest.mark.parametrize('kind,loss', [('SoftmaxLayer', 'nll'), ('SoftmaxLayer', 'nllsq'),
+                                       ('SoftmaxLayer', 'nll35'), ('ExpLossLayer', 'exp'),
+                                       ('HingeLayer', 'hinge')])
+def test_output_losses_match_torch_autograd(kind, loss):
+    """output_views / output_loss (outlayers.py:38-64,105-147) against torch autograd on the
+    formulas as the reference writes them (off the kinks: the tie rule A5 is pinned elsewhere)."""
+    import torch
+    rng = np.random.default_rng(11)
+    B, n, Bg = 9, 6, 18
+    z = rng.standard_normal((B, n))
+    y = rng.integers(0, n, B)
+    feat, lp, probs = O.output_views(kind, z)
+    cost, g = O.output_loss(kind, loss, z, lp, y, Bg)
+    zt = torch.tensor(z, requires_grad=True)
+    rows = torch.arange(B)
+    yt = torch.tensor(y)
+    if kind == 'SoftmaxLayer':
+        lpt = torch.log(torch.softmax(zt, dim=1))
+        pick = lpt[rows, yt]
+        if loss == 'nll':
+            per = -pick
+        elif loss == 'nllsq':
+            per = pick ** 2
+        else:
+            per = torch.clamp(np.log(.35) - pick, min=0)
+        want_feat = lpt
+    elif kind == 'ExpLossLayer':
+        o = zt - zt.mean(dim=1, keepdim=True)
+        per = torch.exp(-o[rows, yt])
+        want_feat = o
+    else:
+        per = torch.clamp(zt + 1 - zt[rows, yt][:, None], min=0).sum(dim=1) / n
+        want_feat = zt
+    total = per.sum() / Bg
+    total.backward()
+    assert abs(cost - total.item()) < 1e-12
+    assert np.allclose(g, zt.grad.numpy(), atol=1e-12)
+    assert np.allclose(feat, want_feat.detach().numpy(), atol=1e-12)
+
+
+def test_meanlayer_colorlayer_and_aux_restatements():
+    import torch
+    rng = np.random.default_rng(12)
+    # ColorLayer (color.py:36-44), written out independently in float64
+    x = rng.random((3, 2, 4, 4)).astype(np.float32) * 2
+    u = rng.uniform(-1, 1, (3, 2, 3)).astype(np.float32)
+    prm = {'balance': 1.4, 'gamma': 1.7, 'maxval': 2}
+    out = O.color_jitter(x, prm, u)
+    e = [np.exp(np.log(a) * u[:, :, k].astype(np.float64))[:, :, None, None]
+         for k, a in enumerate((1.4, 1.7, 1.7))]
+    w = np.clip(x.astype(np.float64) / 2 * e[0], 0, 1) ** e[1]
+    want = (1 - (1 - w) ** e[2]) * 2
+    assert np.max(np.abs(out - want)) < 2e-6
+    # a net with a MeanLayer: whole-step gradients against torch autograd
+    layers = [('InputLayer', {'img_sz': 6, 'num_maps': 2}),
+              ('ConvLayer', {'num_maps': 3, 'filter_sz': 3, 'stride': 1, 'mode': 'same', 'actvn': 'tanh'}),
+              ('MeanLayer', {}),
+              ('SoftmaxLayer', {'n_out': 4})]
+    tp = {'SEED': 3, 'BATCH_SZ': 5, 'INIT_LEARNING_RATE': .1, 'EPOCHS_TO_HALF_RATE': 1}
+    on = O.OracleNet(layers, tp, dtype=np.float64)
+    xb = rng.random((5, 2, 6, 6))
+    yb = rng.integers(0, 4, 5)
+    cost, _ = on.train_step(xb, yb, apply_update=False)
+    W, b = (torch.tensor(t, requires_grad=True) for t in on.spec[1]['params'])
+    Ws, bs = (torch.tensor(t, requires_grad=True) for t in on.spec[3]['params'])
+    a = torch.tanh(torch.nn.functional.conv2d(torch.tensor(xb), torch.flip(W, (2, 3)), padding=1)
+                   + b[None, :, None, None])
+    z = a.mean(dim=(2, 3)) @ Ws + bs
+    loss = -torch.log_softmax(z, dim=1)[torch.arange(5), torch.tensor(yb)].mean()
+    loss.backward()
+    assert abs(cost - loss.item()) < 1e-12
+    for got, want_t in zip(on.last_grads[1] + on.last_grads[3], (W, b, Ws, bs)):
+        assert np.allclose(got, want_t.grad.numpy(), atol=1e-12)
