@@ -65,6 +65,10 @@ const char *tn_last_error(void);
 uint64_t tn_launch_count(void);
 /* refuses anything that is not compute capability 10.x */
 int tn_device_check(int device);
+/* Write the per-step words of the control block (TN_CTL_STEP, _SAMPLE0, _ROW0, _LR_BITS) on
+ * `stream`.  The values are kernel arguments, i.e. captured when the call is enqueued: the host may
+ * run ahead of the device without racing a step that is still queued. */
+int tn_set_ctl(int32_t *ctl, int step, int sample0, int row0, int lr_bits, void *stream);
 
 /* ---- randomness (replaces theano RandomStreams: dropout.py:10-12, inlayers.py:72-141) -------- */
 /* words[s*n + j] = Philox4x32-10 word j of sample (sample0+s); used by tests to pin the stream */
@@ -182,6 +186,22 @@ int tn_convpool_bwd_data(const float *a, const float *pooled, const float *dtop,
                          float *dx, const float *below, int B, int C, int S, int M, int f,
                          int pad_lo, int out_sz, int act, int act_nn, int pool, int pool_out_sz,
                          int act_below, int nn_below, void *stream);
+/* Second-generation path for the shipped geometry (filter 3x3, mode 'valid', pool 2, ReLU-family
+ * or linear activation; conv_small.cu): groups of images per CTA, and ONE backward launch that
+ * rebuilds dL/dz once and produces dW, db and (dx != NULL) dL/d(layer input), with the cross-CTA
+ * sum of the weight gradient folded in (two-level ticket, fixed order: deterministic).
+ * tn_convpool_fprop takes this path by itself when tn_convpool_small_supported() says so.
+ * `workspace` (>= tn_convpool_bwd_workspace_bytes) must be zero-filled once before its first
+ * use; the kernel leaves its ticket counters at zero. */
+int tn_convpool_small_supported(int C, int S, int M, int f, int pad_lo, int out_sz, int act,
+                                int pool, int pool_out_sz);
+size_t tn_convpool_bwd_workspace_bytes(int B, int C, int S, int M, int f, int pad_lo, int out_sz,
+                                       int act, int pool, int pool_out_sz, int need_dx);
+int tn_convpool_bwd(const float *x, const float *a, const float *pooled, const float *dtop,
+                    const float *W, float *dW, float *db, float *dx, const float *below,
+                    void *workspace, int B, int C, int S, int M, int f, int pad_lo, int out_sz,
+                    int act, int act_nn, int pool, int pool_out_sz, int act_below, int nn_below,
+                    void *stream);
 
 /* ---- ConvLayer on tcgen05 tensor cores: bf16 implicit GEMM, NHWC activations (conv_tc.cu) -----
  * For wide layers (C % 64 == 0, M % 64 == 0, mode 'same', output width a power of two <= 128):

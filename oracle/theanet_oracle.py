@@ -510,6 +510,7 @@ class OracleNet:
         rand_gen = np.random.RandomState(training_params['SEED']) if allwts is None else None
         self.batch_sz = training_params['BATCH_SZ']
         self.random = PhiloxRandom()
+        self.tie_source = None  # {PoolLayer index: activations of another implementation}, see train_step
         self.spec = []          # per layer dict: kind, args, params, vel, seeds, shapes
         num_maps, out_sz, n_out = None, None, None
         for li, (name, args) in enumerate(layers):
@@ -865,7 +866,14 @@ class OracleNet:
                     g = g * c['mask']
             elif kind == 'PoolLayer':
                 if g is not None:
-                    g = pool_backward(g, c['pc'])
+                    pc = c['pc']
+                    if self.tie_source and li in self.tie_source:
+                        # tie localisation (tests): route the gradient by the tie pattern of ANOTHER
+                        # implementation's activations (same values up to summation order; which
+                        # mathematically equal conv sums stay equal in float32 depends on that order)
+                        _, pc = pool_forward(np.asarray(self.tie_source[li], dt), L['args']['pool_sz'],
+                                             L['args'].get('ignore_border', False))
+                    g = pool_backward(g, pc)
             elif kind == 'MeanLayer':
                 if g is not None:
                     _, _, h_, w_ = c['in_shape']
@@ -890,6 +898,7 @@ class OracleNet:
             else:
                 g = None        # input layers: no gradient wrt data
         self.last_grads = grads
+        self.last_caches = caches
         if apply_update:
             self.apply_update(grads)
         return cost, logprob

@@ -135,11 +135,16 @@ def test_elastic_layer_matches_the_reference_graph(name):
 # The CUDA path against the same reference-generated vectors (no oracle in between)
 # ------------------------------------------------------------------------------------------------
 TOL_GPU = 1e-3      # BASELINE.json north_star: 1e-3 relative in float32 (observed: ~1e-6)
-# Momentum buffers of networks whose warp duplicates pixels (nearest-neighbour elastic layer): a
-# float32 kernel may break a max-pool tie that the order-independent reference run keeps (see the
-# fixture above); one such window moves the affected conv-gradient entries by a fraction of a
-# per cent for one step.  Filter / dense weights, costs and log-probabilities stay within TOL_GPU.
-TOL_GPU_TIES = 2e-2
+
+
+def tie_window_diff(a_dev, a_ref, p, ignore_border):
+    """(# pool windows whose set of tied maxima differs between two activation tensors, # windows)"""
+    def hits(a):
+        out, (xp, o, S, pp, n) = O.pool_forward(np.asarray(a, np.float32), p, ignore_border)
+        B, C = xp.shape[:2]
+        return xp.reshape(B, C, n, p, n, p) == o[:, :, :, None, :, None]
+    diff = (hits(a_dev) != hits(a_ref)).any(axis=(3, 5))
+    return int(diff.sum()), int(diff.size)
 
 
 def full_weights(g, on, prefix):
@@ -188,31 +193,64 @@ def test_gpu_training_matches_the_reference_graph(name):
     aux = g['aux'] if 'aux' in g.files else None
     assert net.takes_aux() == (aux is not None)
     fn = net.get_trin_model(g['x'], g['y'], aux)
+    B = c['tp']['BATCH_SZ']
+    # Networks whose warp duplicates pixels (nearest-neighbour ElasticLayer: the shipped mnist.prms)
+    # are full of conv sums that are equal mathematically but not operand for operand; whether such
+    # a max-pool tie survives float32 summation depends on the order (see the fixture above), and
+    # the tie-duplicating gradient (A3) follows.  Instead of a looser tolerance the tie pattern is
+    # LOCALISED: the oracle (shown on the CPU to reproduce the reference, order-independent sums)
+    # runs alongside with the device's tie pattern injected (OracleNet.tie_source).  With that the
+    # device must agree with it to TOL_GPU in every tensor, i.e. whatever separates the device from
+    # the reference's numbers is confined to the pool windows counted below.
+    names = [nm for nm, _ in c['layers']]
+    pools = [li for li, nm in enumerate(names) if nm == 'PoolLayer' and names[li - 1] == 'ConvLayer']
+    localise = bool(c['layers'][0][1].get('nearest', False)) and bool(pools)
+    ndiff = nwin = 0
     for s in range(c['steps']):
         if s == c['bump_epoch_at']:
             net.inc_epoch_set_rate()
-        net.inject = device_draws(MR.rand_table(g, c['layers'], 's%d' % s), torch, net.device)
-        cost, feats, lp = fn(s % c['batches'])
+            on.inc_epoch_set_rate()
+        rand = MR.rand_table(g, c['layers'], 's%d' % s)
+        net.inject = device_draws(rand, torch, net.device)
+        b = s % c['batches']
+        cost, feats, lp = fn(b)
         cost, lp = float(cost), np.asarray(lp)
         assert rel(feats, g['feat_%d' % s]) < TOL_GPU, 'features, step %d' % s
         assert abs(cost - g['cost_%d' % s]) <= TOL_GPU * abs(g['cost_%d' % s]), 'cost, step %d' % s
         assert rel(lp, g['logprob_%d' % s]) < TOL_GPU, 'logprob, step %d' % s
+        if localise:
+            acts = {li: net.out[li - 1].cpu().numpy() for li in pools}
+            on.tie_source = acts
+            on.train_step(g['x'][b * B:(b + 1) * B], g['y'][b * B:(b + 1) * B], step=s, rand=rand,
+                          aux=None if aux is None else aux[b * B:(b + 1) * B])
+            for li in pools:
+                d, n = tie_window_diff(acts[li], on.last_caches[li - 1]['a'], c['layers'][li][1]['pool_sz'],
+                                       c['layers'][li][1].get('ignore_border', False))
+                ndiff, nwin = ndiff + d, nwin + n
     torch.cuda.synchronize()
     net.inject = {}
     k = 0
     vel = net.get_velocities()
-    tol_v = TOL_GPU_TIES if c['layers'][0][1].get('nearest', False) else TOL_GPU
     for li, ww in enumerate(net.get_init_params()['allwts']):
         for j, t in enumerate(ww):
-            # biases start at 0 (relu10/relu05, weights.py:64-65): after a few steps they ARE the
-            # accumulated momentum, so they inherit its tolerance
-            tol_w = tol_v if t.ndim == 1 else TOL_GPU
-            assert rel(MR.thin(t), g['w_%d' % k]) < tol_w, 'weights %d' % k
-            if 'v_%d' % k in g.files:
-                assert rel(MR.thin(vel[li][j]), g['v_%d' % k]) < tol_v, 'momentum %d' % k
-            got, want = MR.digest(t), g['wd_%d' % k]
-            assert abs(got[1] - want[1]) <= 4 * tol_w * want[1] + 1e-30
+            if localise:      # against the oracle that shares the device's tie pattern: everything
+                assert rel(t, on.spec[li]['params'][j]) < TOL_GPU, 'weights %d (tie-localised)' % k
+                if on.spec[li]['vel'] is not None:
+                    assert rel(vel[li][j], on.spec[li]['vel'][j]) < TOL_GPU, 'momentum %d (tie-localised)' % k
+            # against the reference's numbers: everything, unless a tie window differed -- then the
+            # momentum buffers (and the biases, which start at 0 and ARE accumulated momentum after a
+            # few steps, weights.py:64-65) carry that window's contribution
+            exact = not (localise and ndiff)
+            if exact or t.ndim != 1:
+                assert rel(MR.thin(t), g['w_%d' % k]) < TOL_GPU, 'weights %d' % k
+                got, want = MR.digest(t), g['wd_%d' % k]
+                assert abs(got[1] - want[1]) <= 4 * TOL_GPU * want[1] + 1e-30
+            if exact and 'v_%d' % k in g.files:
+                assert rel(MR.thin(vel[li][j]), g['v_%d' % k]) < TOL_GPU, 'momentum %d' % k
             k += 1
+    if localise:
+        print('%s: tie pattern differs in %d of %d pool windows' % (name, ndiff, nwin))
+        assert ndiff <= 2e-3 * nwin
     assert k == int(g['n_params'])
     test = net.get_test_model(g['x'], g['y'], aux)
     for b in range(c['batches']):

@@ -228,6 +228,12 @@ FUSED_CASES = [  # B, C, S, M, f, mode, act, pool, ignore_border
     (2, 5, 14, 9, 5, 'same', 'relu', 2, False),
     (700, 4, 13, 20, 3, 'valid', 'relu05', 2, False),   # more images than CTAs
     (2, 1, 64, 4, 3, 'valid', 'relu10', 2, False),      # C5 geometry
+    (37, 3, 10, 6, 3, 'valid', 'relu', 2, True),        # ignore_border, even maps-of-4 padding
+    (5, 2, 33, 5, 3, 'valid', 'linear', 2, False),      # odd side > 32: window overhang guard
+    (1024, 4, 13, 20, 3, 'valid', 'relu05', 2, False),  # the benchmark's conv 2 at its batch size
+    (130, 1, 28, 4, 3, 'valid', 'relu50', 2, False),    # conv 1, groups of images + a ragged tail
+    (9, 4, 31, 20, 3, 'valid', 'relu05', 2, False),     # C5 conv 2
+    (3, 8, 12, 32, 3, 'valid', 'relu05', 2, True),      # padded pixel stride (maps/4 even)
 ]
 
 
@@ -270,7 +276,7 @@ def test_convpool_fused_fwd_bwd(C, case):
         sync()
         res.append((dWd.cpu().numpy(), dbd.cpu().numpy()))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
-    tol = 1e-5 if B < 100 else 1e-4
+    tol = 1e-5 if B < 100 else 1e-4        # float32 sums over up to 1024 x 121 products
     assert rel(res[0][0], dW) < tol and rel(res[0][1], db) < tol
     dxd = torch.zeros_like(xd)
     C.call('tn_convpool_bwd_data', C.ptr(ad), C.ptr(pd), C.ptr(dtd), C.ptr(Wd), C.ptr(dxd), None, B,
@@ -284,6 +290,33 @@ def test_convpool_fused_fwd_bwd(C, case):
     want = O.act_backward('relu07', xnz, xnz, dx)
     got = dxd.cpu().numpy()
     assert rel(got[x != 0], want[x != 0]) < 1e-5
+    # one-launch backward of the second-generation path (conv_small.cu), where it applies
+    geom = (Cin, S, M, f, pad_lo, out_sz, act, p, P)
+    if not C.lib.tn_convpool_small_supported(*geom):
+        assert not (f == 3 and mode == 'valid' and p == 2 and actn != 'tanh')
+        return
+    for need_dx, below in ((1, False), (1, True), (0, False)):
+        nb = C.lib.tn_convpool_bwd_workspace_bytes(B, *geom, need_dx)
+        ws2 = torch.zeros(nb // 4 + 1, device='cuda')
+        res = []
+        for _ in range(3):                     # the ticket counters must come back to zero
+            dWd, dbd = torch.full_like(Wd, 7.0), torch.full_like(bd, 7.0)
+            dxd = torch.full_like(xd, 7.0)
+            C.call('tn_convpool_bwd', C.ptr(xd), C.ptr(ad), C.ptr(pd), C.ptr(dtd), C.ptr(Wd),
+                   C.ptr(dWd), C.ptr(dbd), C.ptr(dxd) if need_dx else None,
+                   C.ptr(xd) if below else None, C.ptr(ws2), B, Cin, S, M, f, pad_lo, out_sz, act,
+                   nn, p, P, *(C.act_code('relu07') if below else (0, 0)), None)
+            sync()
+            res.append((dWd.cpu().numpy(), dbd.cpu().numpy(), dxd.cpu().numpy()))
+        for r in res[1:]:
+            assert all(np.array_equal(u, v) for u, v in zip(res[0], r))
+        assert rel(res[0][0], dW) < tol and rel(res[0][1], db) < tol
+        if need_dx and below:
+            assert rel(res[0][2][x != 0], want[x != 0]) < 1e-5
+        elif need_dx:
+            assert rel(res[0][2], dx) < 1e-5
+        else:
+            assert np.all(res[0][2] == 7.0)
 
 
 def test_convpool_fused_refuses_unsupported(C):

@@ -366,3 +366,123 @@ def test_field_prefetch_survives_alternating_corpora_and_test_calls():
     for a, b in zip(w_g, w_e):
         for t, u in zip(a, b):
             assert np.array_equal(t, u)
+
+
+# --------------------------------------------------------------------------------------------
+# lazy returns: the host runs ahead of the device
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('index_list', [False, True])
+def test_lazy_steps_equal_synchronous_steps(index_list):
+    """lazy=True returns device tensors without synchronising, so the host enqueues many steps
+    ahead.  Per-step scalars travel as launch arguments (tn_set_ctl) and index vectors through an
+    event-guarded ring of pinned buffers, so N lazy steps equal N synchronous steps bit for bit
+    (a pinned control block read by an in-graph copy could be overwritten by a later step)."""
+    from theanet_b200.neuralnet import NeuralNet
+    B, N = 64, 40
+    prms = load_prms('mnist.prms', B, 28)
+    x, y = synth(B * 8, 1, 28, 10)
+    order = np.random.default_rng(9).permutation(8)
+    perm = np.random.default_rng(10).permutation(B * 8).astype(np.int32)
+
+    def arg(s):
+        i = int(order[s % 8])
+        return perm[i * B:(i + 1) * B] if index_list else i
+
+    outs = []
+    for lazy in (False, True):
+        p = copy.deepcopy(prms)
+        net = NeuralNet(p['layers'], p['training_params'])
+        fn = net.get_trin_model(x, y, take_index_list=index_list, lazy=lazy)
+        costs = []
+        for s in range(N):
+            if s == N // 2:
+                net.inc_epoch_set_rate()          # a learning-rate change in mid-flight
+            c, _, lp = fn(arg(s))
+            costs.append(c.clone() if lazy else c)  # lazy: the device scalar of THAT step
+        torch.cuda.synchronize()
+        costs = [float(c.item()) if lazy else float(c) for c in costs]
+        outs.append((costs, net.get_init_params()['allwts'], net.get_velocities()))
+    assert outs[0][0] == outs[1][0]
+    for k in (1, 2):
+        for a, b in zip(outs[0][k], outs[1][k]):
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)
+
+
+# --------------------------------------------------------------------------------------------
+# the benchmark's data regime: 80 % exactly-zero pixels, max-pool ties everywhere
+# --------------------------------------------------------------------------------------------
+def tie_windows(a_dev, a_ref, p=2):
+    """Number of pool windows whose tie pattern (set of elements equal to the window max)
+    differs between two activation tensors, and the number of windows."""
+    def hits(a):
+        out, (xp, o, S, pp, n) = O.pool_forward(a, p, False)
+        B, C = xp.shape[:2]
+        return xp.reshape(B, C, n, p, n, p) == o[:, :, :, None, :, None]
+    ha, hb = hits(a_dev), hits(a_ref)
+    diff = (ha != hb).any(axis=(3, 5))
+    return int(diff.sum()), int(diff.size)
+
+
+def run_tie_localised(prms, x, y, steps, pools, **net_kw):
+    """Train on data full of exact ties.  Which mathematically equal convolution sums stay equal in
+    float32 depends on the summation order, so the CUDA kernels and the NumPy oracle may route the
+    max-pool gradient of a few windows differently (assumption A3; no order is canonical).  The
+    oracle is therefore told, per step, the tie pattern of the DEVICE's activations
+    (OracleNet.tie_source): with that, everything must agree to 1e-3 -- i.e. the whole difference
+    between the two implementations is confined to those windows.  Returns the window counts."""
+    from theanet_b200.neuralnet import NeuralNet
+    p_dev, p_cpu = copy.deepcopy(prms), copy.deepcopy(prms)
+    net = NeuralNet(p_dev['layers'], p_dev['training_params'], **net_kw)
+    on = O.OracleNet(p_cpu['layers'], p_cpu['training_params'])
+    B = prms['training_params']['BATCH_SZ']
+    fn = net.get_trin_model(x, y)
+    nb = len(x) // B
+    ndiff = nwin = 0
+    for s in range(steps):
+        i = s % nb
+        cost, _, lp = fn(i)
+        acts = {li: net.out[li - 1].cpu().numpy() for li in pools}
+        on.tie_source = acts
+        ocost, olp = on.train_step(x[i * B:(i + 1) * B], y[i * B:(i + 1) * B], step=s, sample0=0)
+        assert abs(cost - ocost) <= TOL * abs(ocost), (s, cost, ocost)
+        assert rel(lp, olp) < TOL, (s, rel(lp, olp))
+        for li in pools:
+            a_ref = on.last_caches[li - 1]['a']
+            assert rel(acts[li], a_ref) < 1e-5, (s, li)
+            d, n = tie_windows(acts[li], a_ref)
+            ndiff, nwin = ndiff + d, nwin + n
+        for li, (gg, og) in enumerate(zip(net.get_gradients(), on.last_grads)):
+            for k, u in enumerate(gg):
+                assert rel(u, og[k]) < TOL, 'step {} grad layer {} tensor {}: {}'.format(s, li, k, rel(u, og[k]))
+    compare_nets(net, on, 'tie-localised, after {} steps'.format(steps))
+    return net, ndiff, nwin
+
+
+def test_bench_corpus_at_the_bench_batch_size_tie_localised():
+    """BASELINE configs[1] on bench.py's own corpus (pixels thresholded so that 80 %
+    are exactly 0), 1024 images per step, CUDA graph: the regime in which the tie path of the
+    fused conv+pool backward kernels does real work."""
+    import bench
+    prms = bench.load_prms(1024)
+    x, y = bench.synth_corpus(3 * 1024)
+    net, ndiff, nwin = run_tie_localised(prms, x, y, 3, pools=(2, 4))
+    assert net.head and net.conv_small and net.field_prefetch          # the bench path
+    print('tie pattern differs in {} of {} pool windows'.format(ndiff, nwin))
+    assert ndiff <= 1e-3 * nwin
+
+
+def test_c5_shape_64x64_matches_oracle():
+    """BASELINE configs[4]: mnist.prms topology on 64x64 images (dense 4500 -> 500), elastic
+    distortion on, 512 images per GPU (8 x 512 = the 4096 global batch), three steps."""
+    prms = load_prms('mnist.prms', 512, 64)
+    x, y = synth(1024, 1, 64, 10)
+    net, on, _ = run_pair(prms, x, y, 3, True, check_at=(1, 3))
+    assert net.conv_small and net.head
+
+
+def test_3flat_prms_at_the_bench_batch_size():
+    """BASELINE configs[2]: params/3flat.prms (784 -> 1000 -> 457, no conv) at 1024 images per step."""
+    prms = load_prms('3flat.prms', 1024, 28)
+    x, y = synth(2048, 1, 28, 457)
+    run_pair(prms, x, y, 3, True, check_at=(1, 3))

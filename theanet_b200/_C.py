@@ -46,6 +46,7 @@ SIGNATURES = {
     'tn_last_error': (C.c_char_p, []),
     'tn_launch_count': (C.c_uint64, []),
     'tn_device_check': (_I, [_I]),
+    'tn_set_ctl': (_I, [_P, _I, _I, _I, _I, _P]),
     'tn_philox_words': (_I, [_P, _I, _I, _U64, _I, _I, _I, _P]),
     'tn_elastic_noise': (_I, [_P, _I, _U64, _P, _P]),
     'tn_elastic_field': (_I, [C.POINTER(ElasticPrm), _P, _P, _P, _U64, _P, _P, _P, _P, _P, _P]),
@@ -58,6 +59,9 @@ SIGNATURES = {
     'tn_convpool_bwd_weights_workspace_bytes': (C.c_size_t, [_I] * 4),
     'tn_convpool_bwd_weights': (_I, [_P] * 7 + [_I] * 11 + [_P]),
     'tn_convpool_bwd_data': (_I, [_P] * 6 + [_I] * 13 + [_P]),
+    'tn_convpool_small_supported': (_I, [_I] * 9),
+    'tn_convpool_bwd_workspace_bytes': (C.c_size_t, [_I] * 11),
+    'tn_convpool_bwd': (_I, [_P] * 10 + [_I] * 13 + [_P]),
     'tn_conv2d_tc_supported': (_I, [_I] * 5),
     'tn_nchw_f32_to_nhwc_bf16': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_nhwc_bf16_to_nchw_f32': (_I, [_P, _P, _I, _I, _I, _I, _P]),

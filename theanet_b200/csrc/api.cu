@@ -74,9 +74,29 @@ __global__ void act_bwd_kernel(const float *g, const float *__restrict__ a,
     gz[i] = g[i] * act_bwd_from_out(a[i], act, nn);
 }
 
+__global__ void set_ctl_kernel(int32_t *ctl, int step, int sample0, int row0, int lr_bits) {
+  if (threadIdx.x == 0) {
+    ctl[TN_CTL_STEP] = step;
+    ctl[TN_CTL_SAMPLE0] = sample0;
+    ctl[TN_CTL_ROW0] = row0;
+    ctl[TN_CTL_LR_BITS] = lr_bits;
+  }
+}
+
 }  // namespace tn
 
 using namespace tn;
+
+// The per-step scalars travel as kernel arguments: they are copied when the launch is enqueued, so
+// a host that runs several steps ahead of the device (lazy returns) can never overwrite values a
+// queued step has yet to read -- which a pinned staging buffer read by an in-graph memcpy could.
+extern "C" int tn_set_ctl(int32_t *ctl, int step, int sample0, int row0, int lr_bits,
+                          void *stream) {
+  TN_REQUIRE(ctl, TN_ERR_ARG, "tn_set_ctl: null control block");
+  set_ctl_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(ctl, step, sample0, row0, lr_bits);
+  TN_LAUNCH_CHECK("tn_set_ctl");
+  return TN_OK;
+}
 
 extern "C" int tn_version(void) { return TN_VERSION; }
 

@@ -283,12 +283,16 @@ class NeuralNet():
             l.logprob.tensor = self.logprob
             l.features.tensor = self.feat
             l.y_preds.tensor = self.preds
-        # control block: pinned host copy -> device, refreshed inside the captured graph
+        # control block: per-step scalars, written by a tiny kernel launched ahead of the captured
+        # graph (tn_set_ctl: the values are launch arguments, so a host running ahead of the device
+        # cannot overwrite what a queued step has yet to read).  Index vectors go through a ring
+        # of pinned buffers, each guarded by an event before it is reused.
         pin = self.device.type == 'cuda'
-        self.ctl_host = torch.zeros(_C.CTL_WORDS, dtype=torch.int32, pin_memory=pin)
         self.ctl = torch.zeros(_C.CTL_WORDS, dtype=torch.int32, device=dev)
-        self._ctl_np = self.ctl_host.numpy()
-        self.idx_host = torch.zeros(B, dtype=torch.int32, pin_memory=pin)
+        self._ctl_np = np.zeros(_C.CTL_WORDS, dtype=np.int32)      # host mirror of the last write
+        self._idx_ring = [torch.zeros(B, dtype=torch.int32, pin_memory=pin) for _ in range(8)]
+        self._idx_ev = [None] * len(self._idx_ring)
+        self._idx_k = 0
         self.idx = torch.zeros(B, dtype=torch.int32, device=dev)
         # elastic scratch
         # the (single) distorting ElasticLayer: normally layer 0, possibly behind a Color / Input layer
@@ -329,6 +333,7 @@ class NeuralNet():
         # fused small-channel kernels (conv_fused.cu)
         self.ws = {}
         self.conv_fused = {}
+        self.conv_small = {}
         self.conv_full = {}
         self._plan_conv_tc()
         for li, lyr in enumerate(self.tr_layers):
@@ -347,6 +352,14 @@ class NeuralNet():
                     self.conv_fused[li] = nxt
                     nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
                         B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
+                    # second-generation kernels (conv_small.cu): one backward launch per layer
+                    geom = (lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
+                            lyr.out_sz, lyr.act.code, nxt.pool_sz, nxt.out_sz)
+                    if _C.lib.tn_convpool_small_supported(*geom):
+                        nbs = _C.lib.tn_convpool_bwd_workspace_bytes(B, *geom,
+                                                                     int(self.need_below[li]))
+                        # zero-filled: the kernel's ticket counters start (and are left) at zero
+                        self.conv_small[li] = torch.zeros((nbs + 3) // 4, dtype=f32, device=dev)
                 self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
         # auxiliary-input scratch (auxiliary.py): the gathered (B,2,2) rows, the mixed input, the
         # two LocationInfo activations and, for SoftAuxLayer, their gradients and the cross term
@@ -767,6 +780,21 @@ class NeuralNet():
                 pl = self.conv_fused[li]
                 geom = (B, lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
                         lyr.out_sz, lyr.act.code, lyr.act.nn, pl.pool_sz, pl.out_sz)
+                if fuse and fuse[3] < 1.0:
+                    raise NotImplementedError("dropout-masked dense output feeding a conv")
+                if (li in self.conv_small and self.trainable[li] and
+                        (not fuse or fuse[1] in (_C.ACT_LINEAR, _C.ACT_RELU, _C.ACT_LEAKY))):
+                    # dW, db and dx from one staging of dL/dz (tn_convpool_bwd)
+                    po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, 0, 0)
+                    _C.call('tn_convpool_bwd', _C.ptr(x), _C.ptr(self.out[li]),
+                            _C.ptr(self.out[li + 1]), _C.ptr(g), _C.ptr(lyr.W.tensor),
+                            _C.ptr(lyr.W.grad), _C.ptr(lyr.b.grad),
+                            _C.ptr(dx) if below else None, _C.ptr(po),
+                            _C.ptr(self.conv_small[li]), *geom, ac, nn, st)
+                    if not below:
+                        break
+                    g = dx
+                    continue
                 if self.trainable[li]:
                     with self._wgrad_stream() as sw:
                         _C.call('tn_convpool_bwd_weights', _C.ptr(x), _C.ptr(self.out[li]),
@@ -839,19 +867,33 @@ class NeuralNet():
             g = dx
 
     def _set_ctl(self, row0):
-        c = self._ctl_np                      # numpy view of the pinned control block
+        c = self._ctl_np
         c[_C.CTL_STEP] = self.step_count & 0x7fffffff
         c[_C.CTL_SAMPLE0] = self.dist.rank * self.local_bsz
         c[_C.CTL_ROW0] = int(row0)
         c[_C.CTL_LR_BITS] = int(np.float32(self.cur_learn_rate.get_value()).view(np.int32))
+        if self.device.type == 'cuda':        # eager, stream-ordered ahead of the step's graph
+            _C.call('tn_set_ctl', _C.ptr(self.ctl), int(c[_C.CTL_STEP]), int(c[_C.CTL_SAMPLE0]),
+                    int(c[_C.CTL_ROW0]), int(c[_C.CTL_LR_BITS]), self._stream())
+
+    def _upload_idx(self, ids):
+        """Index vector of this step -> self.idx, through the next pinned ring slot (eager copy,
+        stream-ordered ahead of the step's graph; a slot is reused only after its copy ran)."""
+        k = self._idx_k
+        self._idx_k = (k + 1) % len(self._idx_ring)
+        if self._idx_ev[k] is not None:
+            self._idx_ev[k].synchronize()
+        self._idx_ring[k].copy_(torch.from_numpy(np.ascontiguousarray(ids, dtype=np.int32)))
+        self.idx.copy_(self._idx_ring[k], non_blocking=True)
+        if self.device.type == 'cuda':
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._idx_ev[k] = ev
 
     def _train_launches(self, corpus, idx, labels):
         """Everything one training step enqueues (this is what the CUDA graph captures)."""
         st = self._stream()
         B = self.local_bsz
-        self.ctl.copy_(self.ctl_host, non_blocking=True)
-        if idx is not None:
-            self.idx.copy_(self.idx_host, non_blocking=True)
         self._forward(self.tr_layers, True, corpus, idx, labels)
         if self._prefetching():       # next step's sampling grid, off the critical path
             g_i, g_f = self.el_grids[(self.step_count + 1) & 1]
@@ -910,7 +952,6 @@ class NeuralNet():
             # the graph of step s reads the sampling grid from el_grids[s & 1] and, on a side
             # branch, fills el_grids[(s+1) & 1] for the next step: one graph per parity
             if self._field_step != self.step_count:      # first step, or the sequence was broken
-                self.ctl.copy_(self.ctl_host, non_blocking=True)
                 g_i, g_f = self.el_grids[self.step_count & 1]
                 self._launch_field(self.el_prm, g_i, g_f, self._stream())
             key = key + ('f%d' % (self.step_count & 1),)
@@ -932,7 +973,6 @@ class NeuralNet():
     def _test_launches(self, corpus, idx, labels):
         st = self._stream()
         B = self.local_bsz
-        self.ctl.copy_(self.ctl_host, non_blocking=True)
         self._forward(self.te_layers, False, corpus, idx, labels)
         if self.out_kind == _C.OUT_SOFTMAX:
             _C.call('tn_softmax_test_stats', _C.ptr(self.z), _C.ptr(labels), _C.ptr(idx),
@@ -1090,7 +1130,7 @@ class NeuralNet():
             if take_index_list:
                 ids = np.asarray(indx, dtype=np.int32)[rank * Bl:(rank + 1) * Bl]
                 if host is None:
-                    self.idx_host.copy_(torch.from_numpy(ids))
+                    self._upload_idx(ids)
                     idx, row0 = self.idx, 0
                 else:
                     sel = torch.from_numpy(ids.astype(np.int64))
