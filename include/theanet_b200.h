@@ -191,17 +191,29 @@ int tn_convpool_bwd_data(const float *a, const float *pooled, const float *dtop,
  * rebuilds dL/dz once and produces dW, db and (dx != NULL) dL/d(layer input), with the cross-CTA
  * sum of the weight gradient folded in (two-level ticket, fixed order: deterministic).
  * tn_convpool_fprop takes this path by itself when tn_convpool_small_supported() says so.
+ * tn_convpool_fprop_train is the training-time forward: `a` may be NULL (the un-pooled activations
+ * are then never written) and `tie` (B*M*pool_out^2 bytes), if given, records per pooled cell which
+ * window elements equal the maximum (bit 2*dy+dx) -- Theano's tie-duplicating MaxPoolGrad needs
+ * exactly that.  tn_convpool_bwd takes either `tie` or `a` (then it compares a with pooled).
  * `workspace` (>= tn_convpool_bwd_workspace_bytes) must be zero-filled once before its first
  * use; the kernel leaves its ticket counters at zero. */
 int tn_convpool_small_supported(int C, int S, int M, int f, int pad_lo, int out_sz, int act,
                                 int pool, int pool_out_sz);
+int tn_convpool_fprop_train(const float *x, const float *W, const float *bias, float *a,
+                            float *pooled, uint8_t *tie, int B, int C, int S, int M, int f,
+                            int pad_lo, int out_sz, int act, int act_nn, int pool, int pool_out_sz,
+                            void *stream);
 size_t tn_convpool_bwd_workspace_bytes(int B, int C, int S, int M, int f, int pad_lo, int out_sz,
                                        int act, int pool, int pool_out_sz, int need_dx);
-int tn_convpool_bwd(const float *x, const float *a, const float *pooled, const float *dtop,
-                    const float *W, float *dW, float *db, float *dx, const float *below,
-                    void *workspace, int B, int C, int S, int M, int f, int pad_lo, int out_sz,
-                    int act, int act_nn, int pool, int pool_out_sz, int act_below, int nn_below,
-                    void *stream);
+int tn_convpool_bwd(const float *x, const float *a, const uint8_t *tie, const float *pooled,
+                    const float *dtop, const float *W, float *dW, float *db, float *dx,
+                    const float *below, void *workspace, int B, int C, int S, int M, int f,
+                    int pad_lo, int out_sz, int act, int act_nn, int pool, int pool_out_sz,
+                    int act_below, int nn_below, void *stream);
+
+/* Debug aid (tools/phase_times.py): when buf != NULL, thread 0 of every CTA of tn_convpool_bwd
+ * stores clock64() at its phase boundaries into buf[cta * 64 + slot] (grid <= 1024 CTAs). */
+int tn_convpool_debug_timestamps(long long *buf);
 
 /* ---- ConvLayer on tcgen05 tensor cores: bf16 implicit GEMM, NHWC activations (conv_tc.cu) -----
  * For wide layers (C % 64 == 0, M % 64 == 0, mode 'same', output width a power of two <= 128):
@@ -270,8 +282,14 @@ int tn_dense_bwd_weights(const float *x, const float *g, float *dW, float *db, i
                          int n_out, void *stream);
 /* Dense-path selector (process-wide debugging / benchmarking knob): 0 = auto (tcgen05 tensor cores
  * with 3xTF32 error compensation whenever n_in, n_out are multiples of 4 and n_out > 32, CUDA-core
- * kernels otherwise), 1 = CUDA cores only, 2 = tensor cores with a single TF32 pass, 3 = as 0. */
+ * kernels otherwise; the K range of a product is split over a thread-block cluster whose CTAs
+ * exchange their partial tiles through distributed shared memory, fixed order: deterministic),
+ * 1 = CUDA cores only, 2 = tensor cores with a single TF32 pass, 3 = as 0, 4 = 3xTF32 on the
+ * first-generation kernel (one CTA per tile, fp32 promotion of every 64-deep k-block). */
 int tn_set_dense_mode(int mode);
+/* Debug aid (tools/gemm_phase_times.py): when buf != NULL, every CTA of the cluster split-K kernel
+ * stores clock64() at its phase boundaries into buf[cta * 16 + slot]. */
+int tn_dense_debug_timestamps(long long *buf);
 /* standalone dropout / test-time scaling: out = x * mask * scale (also used on gradients) */
 int tn_dropout_apply(const float *x, float *out, int B, int n, double pkeep, uint64_t seed,
                      const int32_t *ctl, const float *mask_inj, float scale, void *stream);

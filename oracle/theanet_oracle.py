@@ -511,6 +511,8 @@ class OracleNet:
         self.batch_sz = training_params['BATCH_SZ']
         self.random = PhiloxRandom()
         self.tie_source = None  # {PoolLayer index: activations of another implementation}, see train_step
+        self.kink_source = None  # {HiddenLayer index: output of another implementation}, see train_step
+        self.kink_flips = []     # (layer, elements re-signed, max |z| among them, max |z|) per step
         self.spec = []          # per layer dict: kind, args, params, vel, seeds, shapes
         num_maps, out_sz, n_out = None, None, None
         for li, (name, args) in enumerate(layers):
@@ -858,7 +860,20 @@ class OracleNet:
                 W, b = L['params']
                 if 'mask' in c:
                     g = g * c['mask']
-                gz = act_backward(L['actvn'], c['z'], c['a'], g)
+                z = c['z']
+                if self.kink_source and li in self.kink_source:
+                    # kink localisation (tests): the derivative of the ReLU family jumps at z = 0, and
+                    # whether a pre-activation of ~1e-7 lands left or right of it depends on the
+                    # summation order of the product in front.  Take the side the OTHER implementation
+                    # landed on (read off its output where the dropout mask kept it) and record how
+                    # many elements that touched and how close to zero they were.
+                    other = np.asarray(self.kink_source[li], dt).reshape(z.shape)
+                    kept = c['mask'] != 0 if 'mask' in c else np.ones(z.shape, bool)
+                    flip = kept & (other != 0) & (z != 0) & ((other > 0) != (z > 0))
+                    self.kink_flips.append((li, int(flip.sum()), float(np.abs(z[flip]).max()) if flip.any() else 0.,
+                                            float(np.abs(z).max())))
+                    z = np.where(flip, np.copysign(z, other), z)
+                gz = act_backward(L['actvn'], z, c['a'], g)
                 grads[li] = [c['x'].T @ gz, gz.sum(axis=0)]
                 g = (gz @ W.T).reshape(c['in_shape']) if li > first_weighted else None
             elif kind == 'DropOutLayer':

@@ -205,6 +205,7 @@ def test_gpu_training_matches_the_reference_graph(name):
     names = [nm for nm, _ in c['layers']]
     pools = [li for li, nm in enumerate(names) if nm == 'PoolLayer' and names[li - 1] == 'ConvLayer']
     localise = bool(c['layers'][0][1].get('nearest', False)) and bool(pools)
+    net.keep_conv_out = localise    # the localisation reads the un-pooled conv outputs
     ndiff = nwin = 0
     for s in range(c['steps']):
         if s == c['bump_epoch_at']:

@@ -295,14 +295,38 @@ def test_convpool_fused_fwd_bwd(C, case):
     if not C.lib.tn_convpool_small_supported(*geom):
         assert not (f == 3 and mode == 'valid' and p == 2 and actn != 'tanh')
         return
-    for need_dx, below in ((1, False), (1, True), (0, False)):
+    # training-time forward: tie pattern recorded, un-pooled activations optional
+    tie = torch.zeros(B * M * P * P, dtype=torch.uint8, device='cuda')
+    p2 = torch.zeros((B, M, P, P), device='cuda')
+    C.call('tn_convpool_fprop_train', C.ptr(xd), C.ptr(Wd), C.ptr(bd), None, C.ptr(p2), C.ptr(tie),
+           B, Cin, S, M, f, pad_lo, out_sz, act, nn, p, P, None)
+    a2 = torch.zeros((B, M, out_sz, out_sz), device='cuda')
+    C.call('tn_convpool_fprop_train', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(a2), C.ptr(p2), None,
+           B, Cin, S, M, f, pad_lo, out_sz, act, nn, p, P, None)
+    sync()
+    a2n = a2.cpu().numpy()
+    assert rel(a2n, a) < 1e-6
+    pw, (xp_, o_, _, _, n_) = O.pool_forward(a2n, p, ib)
+    assert np.array_equal(p2.cpu().numpy(), pw)
+    hit = (xp_.reshape(B, M, n_, 2, n_, 2) == o_[:, :, :, None, :, None])      # (B,M,P,dy,P,dx)
+    want_tie = (hit[:, :, :, 0, :, 0] * 1 + hit[:, :, :, 0, :, 1] * 2 + hit[:, :, :, 1, :, 0] * 4 +
+                hit[:, :, :, 1, :, 1] * 8).astype(np.uint8)
+    assert np.array_equal(tie.cpu().numpy().reshape(B, M, P, P), want_tie)       # bit-exact
+    # the oracle's own tie pattern as a mask: the backward must not need `a` at all
+    _, (xq, oq, _, _, nq) = O.pool_forward(a, p, ib)
+    hq = (xq.reshape(B, M, nq, 2, nq, 2) == oq[:, :, :, None, :, None])
+    tie_o = dev((hq[:, :, :, 0, :, 0] * 1 + hq[:, :, :, 0, :, 1] * 2 + hq[:, :, :, 1, :, 0] * 4 +
+                 hq[:, :, :, 1, :, 1] * 8).astype(np.uint8))
+    for need_dx, below, use_tie in ((1, False, False), (1, True, True), (0, False, True),
+                                    (1, False, True)):
         nb = C.lib.tn_convpool_bwd_workspace_bytes(B, *geom, need_dx)
         ws2 = torch.zeros(nb // 4 + 1, device='cuda')
         res = []
         for _ in range(3):                     # the ticket counters must come back to zero
             dWd, dbd = torch.full_like(Wd, 7.0), torch.full_like(bd, 7.0)
             dxd = torch.full_like(xd, 7.0)
-            C.call('tn_convpool_bwd', C.ptr(xd), C.ptr(ad), C.ptr(pd), C.ptr(dtd), C.ptr(Wd),
+            C.call('tn_convpool_bwd', C.ptr(xd), None if use_tie else C.ptr(ad),
+                   C.ptr(tie_o) if use_tie else None, C.ptr(pd), C.ptr(dtd), C.ptr(Wd),
                    C.ptr(dWd), C.ptr(dbd), C.ptr(dxd) if need_dx else None,
                    C.ptr(xd) if below else None, C.ptr(ws2), B, Cin, S, M, f, pad_lo, out_sz, act,
                    nn, p, P, *(C.act_code('relu07') if below else (0, 0)), None)
@@ -466,6 +490,69 @@ def test_dense_fwd_bwd(C, case):
     sync()
     want = O.act_backward('relu01', x, prev_a, (g @ W.T) * pm)
     assert rel(dx.cpu().numpy(), want) < 1e-5
+
+
+SPLITK_CASES = [(1024, 720, 500, 'relu01', .5),      # mnist.prms hidden layer at the bench batch size
+                (512, 4500, 500, 'relu01', .5),      # C5: 64x64 images, 4500 -> 500
+                (1024, 784, 1000, 'relu10', .5),     # 3flat.prms
+                (20, 720, 500, 'relu50', 0.),        # the shipped batch size
+                (130, 36, 64, 'linear', 0.),         # one narrow tile, two k-blocks, ragged rows
+                (257, 1000, 132, 'relu05', .25)]     # ragged in every dimension
+
+
+@pytest.mark.parametrize('case', range(len(SPLITK_CASES)))
+def test_dense_split_k_tensor_core_path(C, case):
+    """The default float32 dense path: 128-wide tiles, K split over a thread-block cluster, partial
+    tiles exchanged through distributed shared memory and added in split order
+    (gemm_tc_sk_kernel).  Against float64 NumPy, twice (determinism), and against the
+    first-generation tensor-core path (tn_set_dense_mode(4))."""
+    B, n_in, n_out, actn, pdrop = SPLITK_CASES[case]
+    rng = np.random.default_rng(900 + case)
+    x = rng.standard_normal((B, n_in)).astype(np.float32)
+    W = (rng.standard_normal((n_in, n_out)) / np.sqrt(n_in)).astype(np.float32)
+    b = rng.standard_normal(n_out).astype(np.float32)
+    g = rng.standard_normal((B, n_out)).astype(np.float32)
+    seed, step, s0 = 4711, 5, 1024
+    ctl = make_ctl(C, step=step, sample0=s0)
+    act, nn = C.act_code(actn)
+    x64, W64, g64 = x.astype(np.float64), W.astype(np.float64), g.astype(np.float64)
+    a = O.act_forward(actn, (x64 @ W64 + b).astype(np.float32))
+    mask = philox.bernoulli_mask(seed, philox.PURPOSE_DROPOUT, step, np.arange(s0, s0 + B), n_out,
+                                 1 - pdrop) if pdrop else np.ones_like(a)
+    pm = philox.bernoulli_mask(77, philox.PURPOSE_DROPOUT, step, np.arange(s0, s0 + B), n_in, .5)
+    prev_a = O.act_forward('relu01', x)
+    prev_out = (prev_a * pm).astype(np.float32)
+    xd, Wd, bd, gd, pod = dev(x), dev(W), dev(b), dev(g), dev(prev_out)
+    runs = []
+    for _ in range(2):
+        out = torch.full((B, n_out), 7.0, device='cuda')
+        dx = torch.full((B, n_in), 7.0, device='cuda')
+        dW, db = torch.full_like(Wd, 7.0), torch.full_like(bd, 7.0)
+        C.call('tn_dense_fwd', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(out), B, n_in, n_out, act, nn,
+               1. - pdrop, seed, C.ptr(ctl), None, 1.0, None)
+        C.call('tn_dense_bwd_data', C.ptr(gd), C.ptr(Wd), C.ptr(dx), B, n_in, n_out, C.ptr(pod),
+               *C.act_code('relu01'), .5, 77, C.ptr(ctl), None, None)
+        C.call('tn_dense_bwd_weights', C.ptr(xd), C.ptr(gd), C.ptr(dW), C.ptr(db), B, n_in, n_out,
+               None)
+        sync()
+        runs.append([t.cpu().numpy() for t in (out, dx, dW, db)])
+    for u, v in zip(*runs):
+        assert np.array_equal(u, v)
+    out, dx, dW, db = runs[0]
+    assert np.array_equal(out == 0, (a * mask) == 0) or pdrop == 0
+    assert rel(out, a * mask) < 1e-5
+    assert rel(dx, O.act_backward('relu01', x, prev_a, ((g64 @ W64.T) * pm).astype(np.float32))) < 1e-5
+    assert rel(dW, x64.T @ g64) < 1e-5 and rel(db, g64.sum(0)) < 1e-5
+    # the first-generation path (per-k-block promotion) on the same inputs
+    out1 = torch.zeros((B, n_out), device='cuda')
+    C.call('tn_set_dense_mode', 4)
+    try:
+        C.call('tn_dense_fwd', C.ptr(xd), C.ptr(Wd), C.ptr(bd), C.ptr(out1), B, n_in, n_out, act, nn,
+               1. - pdrop, seed, C.ptr(ctl), None, 1.0, None)
+        sync()
+    finally:
+        C.call('tn_set_dense_mode', 0)
+    assert rel(out, out1.cpu().numpy()) < 1e-5
 
 
 @pytest.mark.parametrize('B,n_in,n_out,pdrop', [(1024, 500, 10, .5), (20, 500, 10, .5), (33, 36, 11, 0.),

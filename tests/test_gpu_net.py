@@ -81,6 +81,24 @@ def compare_nets(net, on, tag):
                 '{} velocity layer {} tensor {}: {}'.format(tag, li, k, r)
 
 
+def relu_hidden_layers(net):
+    """HiddenLayers (not the output layer) whose activation has a kink at zero."""
+    return [li for li, l in enumerate(net.tr_layers[:-1])
+            if type(l).__name__ == 'HiddenLayer' and str(l.actvn).startswith('relu')]
+
+
+def check_kinks(on, n_elems):
+    """The ReLU derivative jumps at z = 0: a pre-activation within rounding of zero may land on
+    either side depending on the summation order of x.W (3xTF32 tensor-core product vs BLAS), and ONE
+    such element moves a weight-gradient column by a few per cent of a typical entry.  The oracle takes
+    the device's side for those elements (OracleNet.kink_source); here: they are a handful, and every
+    one of them is within 1e-5 of zero relative to the layer's largest pre-activation."""
+    for li, n, zmax_flip, zmax in on.kink_flips:
+        assert n <= 2 + 1e-5 * n_elems, (li, n)
+        assert zmax_flip <= 1e-5 * zmax, (li, zmax_flip, zmax)
+    on.kink_flips = []
+
+
 def run_pair(prms, x, y, steps, use_graph, check_at=(1, 2, 5), frozen_first=True, **trin_kw):
     from theanet_b200.neuralnet import NeuralNet
     p_dev, p_cpu = copy.deepcopy(prms), copy.deepcopy(prms)
@@ -91,10 +109,13 @@ def run_pair(prms, x, y, steps, use_graph, check_at=(1, 2, 5), frozen_first=True
     init = net.get_init_params()['allwts']
     nb = len(x) // B
     costs = []
+    kinks = relu_hidden_layers(net)
     for s in range(steps):
         i = s % nb
         cost, feats, lp = fn(i)
+        on.kink_source = {li: net.out[li].cpu().numpy() for li in kinks}
         ocost, olp = on.train_step(x[i * B:(i + 1) * B], y[i * B:(i + 1) * B], step=s, sample0=0)
+        check_kinks(on, B * 1000)
         assert abs(cost - ocost) <= TOL * abs(ocost), 'step {} cost {} vs {}'.format(s, cost, ocost)
         assert rel(lp, olp) < TOL, 'step {} logprob {}'.format(s, rel(lp, olp))
         assert feats is lp or np.array_equal(feats, lp)
@@ -434,6 +455,7 @@ def run_tie_localised(prms, x, y, steps, pools, **net_kw):
     from theanet_b200.neuralnet import NeuralNet
     p_dev, p_cpu = copy.deepcopy(prms), copy.deepcopy(prms)
     net = NeuralNet(p_dev['layers'], p_dev['training_params'], **net_kw)
+    net.keep_conv_out = True        # the comparison below reads the un-pooled conv outputs
     on = O.OracleNet(p_cpu['layers'], p_cpu['training_params'])
     B = prms['training_params']['BATCH_SZ']
     fn = net.get_trin_model(x, y)

@@ -61,7 +61,9 @@ SIGNATURES = {
     'tn_convpool_bwd_data': (_I, [_P] * 6 + [_I] * 13 + [_P]),
     'tn_convpool_small_supported': (_I, [_I] * 9),
     'tn_convpool_bwd_workspace_bytes': (C.c_size_t, [_I] * 11),
-    'tn_convpool_bwd': (_I, [_P] * 10 + [_I] * 13 + [_P]),
+    'tn_convpool_fprop_train': (_I, [_P] * 6 + [_I] * 11 + [_P]),
+    'tn_convpool_bwd': (_I, [_P] * 11 + [_I] * 13 + [_P]),
+    'tn_convpool_debug_timestamps': (_I, [_P]),
     'tn_conv2d_tc_supported': (_I, [_I] * 5),
     'tn_nchw_f32_to_nhwc_bf16': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_nhwc_bf16_to_nchw_f32': (_I, [_P, _P, _I, _I, _I, _I, _P]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     'tn_dense_bwd_data': (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _D, _U64, _P, _P, _P]),
     'tn_dense_bwd_weights': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     'tn_set_dense_mode': (_I, [_I]),
+    'tn_dense_debug_timestamps': (_I, [_P]),
     'tn_subsample2d': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_upsample2d_zero': (_I, [_P, _P, _I, _I, _I, _I, _P]),
     'tn_meanpool_fwd': (_I, [_P, _P, _I, _I, _P]),

@@ -480,7 +480,7 @@ extern "C" int tn_convpool_fprop(const float *x, const float *W, const float *bi
   const char *who = "tn_convpool_fprop";
   TN_REQUIRE(x && W && bias && a && (pooled || !pool), TN_ERR_ARG, "%s: null argument", who);
   if (B > 0 && small_conv_ok(C, S, M, f, pad_lo, out_sz, act, pool, pool_out_sz))   // conv_small.cu
-    return small_fprop(x, W, bias, a, pooled, B, C, S, M, out_sz, act, act_nn, pool_out_sz,
+    return small_fprop(x, W, bias, a, pooled, nullptr, B, C, S, M, out_sz, act, act_nn, pool_out_sz,
                        (cudaStream_t)stream);
   FusedArgs k{};
   int rc = fill_geom(k, B, C, S, M, f, pad_lo, out_sz, pool, pool_out_sz, who);

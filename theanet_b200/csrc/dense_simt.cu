@@ -247,7 +247,8 @@ int g_dense_mode = 0;
 static bool use_tc(int n_in, int n_out, const void *a, const void *b, const void *c) {
   return g_dense_mode != 1 && dense_tc_ok(n_in, n_out, a, b, c);
 }
-static int tc_split() { return g_dense_mode == 2 ? 0 : 1; }
+// 0: one TF32 pass, 1: 3xTF32 cluster split-K (default), 2: first-generation 3xTF32 kernel
+static int tc_split() { return g_dense_mode == 2 ? 0 : (g_dense_mode == 4 ? 2 : 1); }
 
 template <int AMODE, int BMODE, int EPI>
 static int launch_gemm(const GemmArgs &g, bool vec, const char *name, cudaStream_t st) {
@@ -353,8 +354,15 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
   return TN_OK;
 }
 
+// Debug aid (tools/gemm_phase_times.py): when buf != NULL, every CTA of the cluster split-K kernel
+// stores clock64() at its phase boundaries into buf[cta * 16 + slot]
+extern "C" int tn_dense_debug_timestamps(long long *buf) {
+  dense_tc_set_debug(buf);
+  return TN_OK;
+}
+
 extern "C" int tn_set_dense_mode(int mode) {
-  TN_REQUIRE(mode >= 0 && mode <= 3, TN_ERR_ARG, "tn_set_dense_mode: mode must be 0..3");
+  TN_REQUIRE(mode >= 0 && mode <= 4, TN_ERR_ARG, "tn_set_dense_mode: mode must be 0..4");
   g_dense_mode = mode;
   return TN_OK;
 }

@@ -21,6 +21,9 @@ int dense_tc_bwd_data(const float *gr, const float *W, float *dx, int B, int n_i
                       cudaStream_t st);
 int dense_tc_bwd_weights(const float *x, const float *gr, float *dW, int B, int n_in, int n_out,
                          int split, cudaStream_t st);
+// `split`: 0 = one TF32 pass, 1 = 3xTF32 on the cluster split-K kernel, 2 = 3xTF32 on the
+// first-generation kernel (per-k-block promotion)
+void dense_tc_set_debug(long long *buf);
 int tc_make_map_2d(CUtensorMap *map, const float *ptr, int rows, int cols, int ld, int box_cols,
                    int box_rows, int atom32, const char *who);
 

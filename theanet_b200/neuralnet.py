@@ -21,6 +21,7 @@ PyTorch is used for device memory, streams, CUDA graphs and torch.distributed on
 import ctypes
 import os
 from contextlib import contextmanager
+from types import SimpleNamespace
 from functools import reduce
 from operator import mul
 
@@ -144,6 +145,7 @@ class NeuralNet():
 
         self.step_count = 0
         self.inject = {}            # (layer index, 'noise'|'u'|'flip'|'mask') -> device tensor
+        self.keep_conv_out = False  # also write the un-pooled output of fused conv+pool layers when training
         self.debug_elastic = False
         self._allocate()
 
@@ -347,19 +349,29 @@ class NeuralNet():
                     full = (B, lyr.num_maps, lyr.full_sz, lyr.full_sz)
                     self.conv_full[li] = (torch.empty(full, dtype=f32, device=dev),
                                           torch.empty(full, dtype=f32, device=dev))
-                if (self.fuse_conv and lyr.stride == 1 and isinstance(nxt, PoolLayer)
-                        and self._fused_conv_ok(lyr)):
-                    self.conv_fused[li] = nxt
-                    nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
-                        B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
-                    # second-generation kernels (conv_small.cu): one backward launch per layer
+                if self.fuse_conv and lyr.stride == 1 and isinstance(nxt, PoolLayer):
+                    # second-generation kernels (conv_small.cu): groups of images per CTA, one
+                    # backward launch per layer; else the first-generation fused kernels
                     geom = (lyr.num_prev_maps, lyr.in_sz, lyr.num_maps, lyr.filter_sz, lyr.pad_lo,
                             lyr.out_sz, lyr.act.code, nxt.pool_sz, nxt.out_sz)
-                    if _C.lib.tn_convpool_small_supported(*geom):
+                    small = bool(_C.lib.tn_convpool_small_supported(*geom))
+                    gen1 = self._fused_conv_ok(lyr)
+                    if small or gen1:
+                        self.conv_fused[li] = nxt
+                    if gen1:
+                        nb = max(nb, _C.lib.tn_convpool_bwd_weights_workspace_bytes(
+                            B, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz))
+                    if small:
                         nbs = _C.lib.tn_convpool_bwd_workspace_bytes(B, *geom,
                                                                      int(self.need_below[li]))
-                        # zero-filled: the kernel's ticket counters start (and are left) at zero
-                        self.conv_small[li] = torch.zeros((nbs + 3) // 4, dtype=f32, device=dev)
+                        # zero-filled: the kernel's ticket counters start (and are left) at zero;
+                        # tie: which window elements equal the pooled maximum, written by the
+                        # training forward, read by the backward kernel instead of out[li]
+                        self.conv_small[li] = SimpleNamespace(
+                            ws=torch.zeros((nbs + 3) // 4, dtype=f32, device=dev),
+                            tie=torch.zeros(B * lyr.num_maps * nxt.out_sz ** 2, dtype=torch.uint8,
+                                            device=dev),
+                            tie_valid=False)
                 self.ws[li] = torch.empty((nb + 3) // 4, dtype=f32, device=dev)
         # auxiliary-input scratch (auxiliary.py): the gathered (B,2,2) rows, the mixed input, the
         # two LocationInfo activations and, for SoftAuxLayer, their gradients and the cross term
@@ -420,7 +432,6 @@ class NeuralNet():
         """conv_tc[li]: buffers of ConvLayer li (and the PoolLayer above it) on the tcgen05 bf16
         implicit-GEMM kernels (conv_tc.cu).  Activations inside the stack are NHWC bfloat16; they
         are converted from / to the float32 NCHW tensors of the neighbouring layers at its ends."""
-        from types import SimpleNamespace
         self.conv_tc = {}
         if str(self.tr_prms.get('CONV_DTYPE', 'float32')).lower() not in ('bf16', 'bfloat16'):
             return
@@ -568,6 +579,15 @@ class NeuralNet():
                     Po = O_ // 2 if t.pool else O_
                     _C.call('tn_nhwc_bf16_to_nchw_f32', _C.ptr(src), _C.ptr(self.out[t.out_idx]), B,
                             M_, Po, Po, st)
+            elif isinstance(lyr, ConvLayer) and li in self.conv_small and train:
+                # training forward: the tie pattern goes to the backward kernel; the un-pooled
+                # activations are only written on request (keep_conv_out) -- nothing reads them
+                pl, sm = self.conv_fused[li], self.conv_small[li]
+                _C.call('tn_convpool_fprop_train', _C.ptr(x), _C.ptr(lyr.W.tensor),
+                        _C.ptr(lyr.b.tensor), _C.ptr(out) if self.keep_conv_out else None,
+                        _C.ptr(self.out[li + 1]), _C.ptr(sm.tie), B, lyr.num_prev_maps, lyr.in_sz,
+                        lyr.num_maps, lyr.filter_sz, lyr.pad_lo, lyr.out_sz, lyr.act.code,
+                        lyr.act.nn, pl.pool_sz, pl.out_sz, st)
             elif isinstance(lyr, ConvLayer) and li in self.conv_fused:
                 pl = self.conv_fused[li]
                 _C.call('tn_convpool_fprop', _C.ptr(x), _C.ptr(lyr.W.tensor),
@@ -782,15 +802,17 @@ class NeuralNet():
                         lyr.out_sz, lyr.act.code, lyr.act.nn, pl.pool_sz, pl.out_sz)
                 if fuse and fuse[3] < 1.0:
                     raise NotImplementedError("dropout-masked dense output feeding a conv")
-                if (li in self.conv_small and self.trainable[li] and
+                if (li in self.conv_small and
                         (not fuse or fuse[1] in (_C.ACT_LINEAR, _C.ACT_RELU, _C.ACT_LEAKY))):
-                    # dW, db and dx from one staging of dL/dz (tn_convpool_bwd)
+                    # dW, db and dx from one staging of dL/dz (tn_convpool_bwd); the tie pattern
+                    # comes from this step's forward kernel
                     po, ac, nn = (fuse[0], fuse[1], fuse[2]) if fuse else (None, 0, 0)
-                    _C.call('tn_convpool_bwd', _C.ptr(x), _C.ptr(self.out[li]),
+                    sm = self.conv_small[li]
+                    _C.call('tn_convpool_bwd', _C.ptr(x), None, _C.ptr(sm.tie),
                             _C.ptr(self.out[li + 1]), _C.ptr(g), _C.ptr(lyr.W.tensor),
                             _C.ptr(lyr.W.grad), _C.ptr(lyr.b.grad),
-                            _C.ptr(dx) if below else None, _C.ptr(po),
-                            _C.ptr(self.conv_small[li]), *geom, ac, nn, st)
+                            _C.ptr(dx) if below else None, _C.ptr(po), _C.ptr(sm.ws), *geom, ac, nn,
+                            st)
                     if not below:
                         break
                     g = dx

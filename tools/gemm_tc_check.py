@@ -1,6 +1,7 @@
 """GPU check of the tcgen05 dense path against float64 numpy: errors and CUDA-event timings of
 tn_dense_fwd / tn_dense_bwd_data / tn_dense_bwd_weights per dense mode (1 = CUDA cores,
-2 = tensor cores single TF32 pass, 3 = tensor cores 3xTF32).   python tools/gemm_tc_check.py"""
+2 = tensor cores single TF32 pass, 3 = tensor cores 3xTF32 (cluster split-K), 4 = first-generation
+3xTF32 kernel), plus a cuBLAS yardstick through torch.matmul (this tool only).   python tools/gemm_tc_check.py"""
 import json
 import os
 import sys
@@ -62,7 +63,7 @@ def main():
         want_f = x.astype(np.float64) @ W.astype(np.float64) + b
         want_dx = g.astype(np.float64) @ W.astype(np.float64).T
         want_dW = x.astype(np.float64).T @ g.astype(np.float64)
-        for mode in (1, 2, 3):
+        for mode in (1, 2, 4, 3):     # 3 = default (cluster split-K 3xTF32), 4 = first generation
             C.call('tn_set_dense_mode', mode)
 
             def f_fwd():
@@ -86,7 +87,20 @@ def main():
                 res[name + '_err'] = rel(t.cpu().numpy().astype(np.float64), want)
                 res[name + '_us'] = round(timeit(fn), 2)
             print(json.dumps(res), flush=True)
-    C.call('tn_set_dense_mode', 0)
+        C.call('tn_set_dense_mode', 0)
+        # yardstick (this tool only, never the product): cuBLAS through torch.matmul
+        for tf32 in (False, True):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            res = {'shape': [B, n_in, n_out], 'mode': 'cuBLAS ' + ('tf32' if tf32 else 'fp32')}
+            for name, fn, want in (('fwd', lambda: torch.matmul(xd, Wd, out=out), want_f - b),
+                                   ('dx', lambda: torch.matmul(gd, Wd.t(), out=dx), want_dx),
+                                   ('dW', lambda: torch.matmul(xd.t(), gd, out=dW), want_dW)):
+                r = fn()
+                torch.cuda.synchronize()
+                res[name + '_err'] = rel(r.cpu().numpy().astype(np.float64), want)
+                res[name + '_us'] = round(timeit(fn), 2)
+            print(json.dumps(res), flush=True)
+        torch.backends.cuda.matmul.allow_tf32 = False
 
 
 if __name__ == '__main__':
