@@ -29,38 +29,61 @@ PER_GPU_BATCH = 1024
 IMG, NCLS = 28, 10
 CORPUS_BATCHES = 64                # 64 x 1024 x 3136 B = 205 MB per GPU-share: larger than L2
 WORKLOAD = "params/mnist.prms synthetic 28x28x1, batch 1024 per GPU, fp32 (BASELINE configs[1])"
+# The other single-GPU configurations of BASELINE.json, reported next to the headline in
+# `other_configs` (each with its own step time and step-level roofline); `nb` minibatches per GPU
+# are cycled so that the corpus share exceeds the 126 MB L2.
+CONFIGS = {
+    'c2': dict(prms='mnist.prms', img=28, maps=1, ncls=10, per_gpu=1024, nb=64, bf16=False, dtype='f32',
+               workload=WORKLOAD),
+    'c3': dict(prms='3flat.prms', img=28, maps=1, ncls=457, per_gpu=1024, nb=64, bf16=False, dtype='f32',
+               workload="params/3flat.prms (784 -> 1000 -> 457, no conv) synthetic 28x28x1, batch 1024 "
+                        "per GPU, fp32 (BASELINE configs[2])"),
+    'c4': dict(prms='cifar3conv.prms', img=32, maps=3, ncls=10, per_gpu=1024, nb=12, bf16=True, dtype='bf16',
+               workload="CIFAR-shaped 32x32x3, 3-conv params/cifar3conv.prms, bf16 tensor-core conv "
+                        "stack, batch 1024 per GPU (BASELINE configs[3])"),
+    'c5': dict(prms='mnist.prms', img=64, maps=1, ncls=10, per_gpu=512, nb=20, bf16=False, dtype='f32',
+               workload="ElasticLayer on, 64x64x1 synthetic, mnist.prms topology, batch 512 per GPU "
+                        "(4096 at 8 GPUs), fp32 (BASELINE configs[4])"),
+}
 # algorithmic work of one training step, per image (layer-boundary convention)
 FLOP_PER_IMG = 2810064
 BYTES_PER_IMG = 181144
 PARAM_BYTES_PER_STEP = 8 * 4 * 366290
 
 
-def load_prms(global_batch):
-    with open(os.path.join(ROOT, 'params', 'mnist.prms')) as f:
+def load_prms(global_batch, cfg='c2'):
+    c = CONFIGS[cfg]
+    with open(os.path.join(ROOT, 'params', c['prms'])) as f:
         p = ast.literal_eval(f.read())
     p['training_params'].update(SEED=555555, BATCH_SZ=global_batch)
-    p['layers'][0][1]['img_sz'] = IMG
+    if c['bf16']:
+        p['training_params']['CONV_DTYPE'] = 'bfloat16'
+    p['layers'][0][1]['img_sz'] = c['img']
     return p
 
 
-def synth_corpus(n):
+def synth_corpus(n, cfg='c2'):
     """uniform pixels thresholded so ~80% are exactly 0, uniform labels."""
+    c = CONFIGS[cfg]
     rng = np.random.default_rng(1234)
-    x = rng.random((n, 1, IMG, IMG), dtype=np.float32)
+    x = rng.random((n, c['maps'], c['img'], c['img']), dtype=np.float32)
     x *= (x > .8)
-    y = rng.integers(0, NCLS, n).astype(np.int32)
+    y = rng.integers(0, c['ncls'], n).astype(np.int32)
     return x, y
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind each entry point, from
-# the committed `ncu --set full` capture of this workload (profiles/r1_ncu_full_summary.md;
-# batch 1024).  Writes are 0 there: outputs stay in the 126 MB L2 between kernels.
-NCU_TRAFFIC = {
-    ('tn_dense_fwd', 0): 4529920, ('tn_dense_bwd_weights', 0): 5087488, ('tn_dense_bwd_data', 0): 3619328,
-    ('tn_convpool_fprop', 0): 3288576, ('tn_convpool_fprop', 1): 2849024,
-    ('tn_convpool_bwd_weights', 0): 18605568, ('tn_convpool_bwd_weights', 1): 19850752,
-    ('tn_convpool_bwd_data', 0): 15840256,
-}
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernel behind each entry point,
+    from profiles/r2_kernels.json -- written by tools/profile_kernels.py out of an `ncu --set full`
+    capture of THIS workload; the file records the git revision of the binaries it profiled.
+    Returns ({(entry point, ordinal): bytes}, provenance)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r2_kernels.json')) as f:
+            d = json.load(f)
+        tr = {(k['entry'], int(k['ordinal'])): k['dram_bytes'] for k in d['kernels'] if k.get('entry')}
+        return tr, "profiles/r2_kernels.json (ncu --set full, git {})".format(d.get('git', '?'))
+    except Exception:
+        return {}, None
 
 
 def peaks():
@@ -144,17 +167,18 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    batch = 256                                   # bounded sample: 256-image minibatches
-    steps = max(1, args.steps)
+    batch = PER_GPU_BATCH                         # same minibatch size as the GPU arm
+    steps = max(1, min(args.steps, 24))           # bounded sample: a step takes ~0.15 s on 16 cores
     v, n, dt = cpu_step_time(None, batch, steps=steps, warmup=max(1, min(args.warmup, 3)))
     cores = host_threads()
     sample = "{} oracle train steps of {} images (numpy/BLAS im2col+SGEMM restatement)".format(n, batch)
     line = {
         "impl": "reference", "metric": "images/sec", "value": v, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / n, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "cpu_sample_batch": batch},
+        "config": {"workload": WORKLOAD, "global_batch": batch, "per_gpu_batch": batch,
+                   "cpu_sample_steps": n, "same_config": True},
         "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -186,7 +210,16 @@ def stage_work(net):
             a = B * l.num_maps * l.out_sz ** 2 * 4
             wt = l.W.size * 4
             fl = 2 * B * l.num_maps * l.out_sz ** 2 * l.num_prev_maps * l.filter_sz ** 2
-            if li in net.conv_fused:
+            if li in getattr(net, 'conv_small', {}):
+                # second-generation kernels: the un-pooled activations never reach HBM; the forward
+                # writes the pooled map + one tie byte per pooled cell, the single backward launch
+                # reads x, tie, pooled, dL/dpooled, W and writes dW, db (and dx)
+                p = B * l.num_maps * net.conv_fused[li].out_sz ** 2 * 4
+                fwd.append(('tn_convpool_fprop_train', xin + p + p // 4 + wt, fl))
+                bwd.append((li, [('tn_convpool_bwd', xin + p // 4 + 2 * p + 2 * wt +
+                                  (xin if net.need_below[li] else 0),
+                                  fl * (2 if net.need_below[li] else 1))]))
+            elif li in net.conv_fused:
                 p = B * l.num_maps * net.conv_fused[li].out_sz ** 2 * 4
                 fwd.append(('tn_convpool_fprop', xin + a + p + wt, fl))
                 bwd.append((li, [('tn_convpool_bwd_weights', xin + a + 2 * p + wt, fl)] +
@@ -259,6 +292,131 @@ def profile_stages(net, fn, nb, reps):
         out[k] = float(np.mean(ts))
     return out
 
+
+
+def step_work(net):
+    """(bytes, flops) of one training step in the layer-boundary convention of SURVEY.md 8(d): every
+    layer reads its input and writes its output once in the forward pass, reads dL/dout (+ what its
+    derivative needs) and writes dL/din in the backward pass; 32 bytes per parameter (two reads by
+    the products, gradient write, theta/velocity/gradient read and theta/velocity write of the
+    update); 2 FLOP per multiply-add, three products per weighted layer (two for the first)."""
+    from theanet_b200.layer import ConvLayer, HiddenLayer
+    B = net.local_bsz
+    byts = fl = 0
+    first = True
+    for li, l in enumerate(net.tr_layers):
+        o = net.out[li]
+        if o is None or li == 0:
+            if li == 0 and o is not None:
+                byts += 2 * o.numel() * o.element_size()          # corpus read + warped image write
+            continue
+        n_in = net.out[li - 1].numel() * net.out[li - 1].element_size() if net.out[li - 1] is not None else 0
+        n_out = o.numel() * o.element_size()
+        if li in getattr(net, 'conv_tc', {}):                    # bf16 NHWC inside the tensor-core stack
+            n_out //= 2
+        byts += n_in + n_out                                       # forward
+        byts += 2 * n_out + (n_in if net.need_below[li] else 0)    # backward
+        macs = 0
+        if isinstance(l, ConvLayer):
+            macs = B * l.num_maps * l.out_sz ** 2 * l.num_prev_maps * l.filter_sz ** 2
+        elif isinstance(l, HiddenLayer):
+            macs = B * l.n_in * l.n_out
+        if macs:
+            fl += 2 * macs * (2 if first else 3)
+            first = False
+    byts += 32 * int(net.theta.numel())
+    return byts, fl
+
+
+def time_config(cfg, world, rank, dev, ctx, steps, warm, barrier, max_over_ranks):
+    """One BASELINE configuration through the same timed loop as the headline: `warm` untimed steps,
+    `steps` steps between CUDA events, max over ranks.  Returns the `other_configs` entry."""
+    import torch
+    from theanet_b200.neuralnet import NeuralNet
+    c = CONFIGS[cfg]
+    gb = c['per_gpu'] * world
+    prms = load_prms(gb, cfg)
+    x, y = synth_corpus(c['nb'] * gb, cfg)
+    net = NeuralNet(prms['layers'], prms['training_params'], device=dev, dist=ctx)
+    fn = net.get_trin_model(x, y, lazy=True)
+    for s in range(warm):
+        fn(s % c['nb'])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        fn((warm + s) % c['nb'])
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    cost = float(net.cost.item())
+    assert np.isfinite(cost), (cfg, cost)
+    byts, fl = step_work(net)
+    hbm, tfl, which = peaks()
+    t_hbm, t_tc = byts / (hbm * 1e9), fl / (tfl * 1e12)
+    bound = 'tensor' if (c['bf16'] and t_tc > t_hbm) else 'hbm'
+    ach = (fl / (ms * 1e-3) / 1e12) if bound == 'tensor' else (byts / (ms * 1e-3) / 1e9)
+    peak = tfl if bound == 'tensor' else hbm
+    out = {"workload": c['workload'], "dtype": c['dtype'], "global_batch": gb, "per_gpu_batch": c['per_gpu'],
+           "ms_per_step": ms, "images_per_s": gb / (ms * 1e-3), "steps": steps, "warmup": warm,
+           "launches_per_step": int(net.launches.get('train', 0)), "cost_after": cost,
+           "l2": "{} minibatches ({} MB per GPU) cycled".format(
+               c['nb'], c['nb'] * c['per_gpu'] * c['maps'] * c['img'] ** 2 * 4 // 10 ** 6),
+           "roofline": {"scope": "whole step, layer-boundary convention (SURVEY.md 8d)", "bound": bound,
+                        "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == 'tensor' else "GB/s",
+                        "frac": ach / peak, "algorithmic_bytes_per_step": byts,
+                        "algorithmic_flops_per_step": fl,
+                        "hbm_frac": byts / (ms * 1e-3) / 1e9 / hbm,
+                        "tensor_frac": fl / (ms * 1e-3) / 1e12 / tfl, "peak_source": which}}
+    del fn, net
+    torch.cuda.empty_cache()
+    return out
+
+
+def dp_parity(world, rank, dev, ctx, steps=3):
+    """Data-parallel correctness where the driver can see it: N ranks train `steps`
+    steps of the headline workload from a fixed seed; rank 0 then trains the SAME global minibatches
+    alone.  Reports the worst per-tensor deviation of the N-rank parameters from the single-rank
+    ones (they differ only by the order of the gradient sum) and whether all replicas hold
+    bit-identical parameters."""
+    import torch
+    import torch.distributed as dist
+    from theanet_b200.neuralnet import NeuralNet, DistContext
+    gb = PER_GPU_BATCH * world
+    x, y = synth_corpus(steps * gb)
+
+    def run(context):
+        prms = load_prms(gb)
+        net = NeuralNet(prms['layers'], prms['training_params'], device=dev, dist=context)
+        fn = net.get_trin_model(x, y, lazy=True)
+        for s in range(steps):
+            fn(s)
+        torch.cuda.synchronize(dev)
+        return net
+
+    net_n = run(ctx)
+    theta_n = net_n.theta.detach().clone()
+    digest = torch.stack([theta_n.double().sum(), theta_n.view(torch.int32).long().sum().double()])
+    all_d = [torch.zeros_like(digest) for _ in range(world)]
+    dist.all_gather(all_d, digest)
+    identical = all(bool(torch.equal(all_d[0], d)) for d in all_d)
+    res = None
+    if rank == 0:
+        net_1 = run(DistContext())
+        worst = 0.0
+        for seg_n, seg_1 in zip(net_n.get_init_params()['allwts'], net_1.get_init_params()['allwts']):
+            for u, v in zip(seg_n, seg_1):
+                d = float(np.max(np.abs(u.astype(np.float64) - v)) / max(float(np.max(np.abs(v))), 1e-30))
+                worst = max(worst, d)
+        res = {"steps": steps, "global_batch": gb, "max_rel": worst, "replicas_identical": identical,
+               "tolerance": 1e-3,
+               "what": "parameters after {} steps on {} ranks vs one rank on the same global "
+                       "minibatches (max |a-b| / max |b| per tensor, worst tensor)".format(steps, world)}
+        del net_1
+    dist.barrier()
+    del net_n
+    torch.cuda.empty_cache()
+    return res
 
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -351,6 +509,7 @@ def run_ours(args):
         stages = profile_stages(net, fn_prof, nb, reps=10)
         if rank == 0:
             work = stage_work(net)
+            traffic, traffic_src = ncu_traffic()
             total_ms = sum(stages.values())
             (name, k), t_ms = max(stages.items(), key=lambda kv: kv[1])
             li = k
@@ -361,8 +520,8 @@ def run_ours(args):
                 ach = byts / (t_ms * 1e-3) / 1e9
                 roof = {"bound": "hbm", "kernel": "{} (call #{} of the step)".format(name, li),
                         "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                        "traffic": NCU_TRAFFIC.get((name, k)) if world == 1 else None,
-                        "traffic_source": "profiles/r1_ncu_full_summary.md (ncu --set full, r1b kernels)",
+                        "traffic": traffic.get((name, k)) if world == 1 else None,
+                        "traffic_source": traffic_src,
                         "launch_ms": t_ms, "algorithmic_bytes": byts,
                         "algorithmic_flops": fl,
                         "achieved_tflops": (fl / (t_ms * 1e-3) / 1e12) if fl else None,
@@ -373,6 +532,21 @@ def run_ours(args):
                         "unit": "GB/s", "frac": None, "traffic": None, "launch_ms": t_ms,
                         "peak_source": which, "step_share": share}
     barrier()
+
+    # ---- the other BASELINE configurations, and data-parallel parity at N > 1 ---------------------
+    del fn, fn_e2e
+    torch.cuda.empty_cache()
+    others = {}
+    if not args.no_other:
+        k_other = max(10, min(args.steps, 50))
+        for cfg in (('c3', 'c4', 'c5') if world == 1 else ('c4', 'c5')):
+            try:
+                others[cfg] = time_config(cfg, world, rank, dev, ctx, k_other, warm, barrier,
+                                          max_over_ranks)
+            except Exception as ex:                       # a config must not cost the headline
+                others[cfg] = {"error": "{}: {}".format(type(ex).__name__, ex)}
+                barrier()
+    parity = dp_parity(world, rank, dev, ctx) if world > 1 else None
 
     if rank != 0:
         if world > 1:
@@ -385,10 +559,11 @@ def run_ours(args):
     cpu_v, cpu_n, cpu_dt = (None, 0, 0.0)
     cpu = None
     if world == 1:
-        cpu_v, cpu_n, cpu_dt = cpu_step_time(12.0, 256)
+        cpu_v, cpu_n, cpu_dt = cpu_step_time(12.0, PER_GPU_BATCH)
         cpu = {"value": cpu_v, "unit": "images/s", "cores": host_threads(), "kind": "port",
-               "sample": "{} oracle train steps of 256 images in {:.1f} s (numpy/BLAS "
-                         "restatement of the Theano CPU path)".format(cpu_n, cpu_dt)}
+               "sample": "{} oracle train steps of {} images in {:.1f} s (numpy/BLAS "
+                         "restatement of the Theano CPU path, same minibatch size as the GPU arm)".format(
+                             cpu_n, PER_GPU_BATCH, cpu_dt)}
 
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world,
@@ -404,7 +579,7 @@ def run_ours(args):
                                   "fused into the update kernel over CUDA-IPC peer memory (NVLink)"
                                   if net.dp_fused else "NCCL all-reduce of the flat gradient buffer")},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "cpu_baseline": cpu, "other_configs": others, "dp_parity": parity,
         "step_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes,
                           "achieved": step_gbs, "peak": hbm, "unit": "GB/s",
                           "frac": step_gbs / hbm, "flop_per_img": FLOP_PER_IMG},
@@ -420,6 +595,7 @@ def main():
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--no-other', action='store_true', help="skip other_configs (C3/C4/C5)")
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -17,7 +17,8 @@ LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libtheanet_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
-         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+         '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr', '-Xptxas', '-v'] + \
+    os.environ.get('TN_NVCC_EXTRA', '').split()
 
 
 def sources():

@@ -3,12 +3,22 @@
 // activation backward used when a conv layer feeds a dense layer directly.
 #include <stdarg.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace tn {
 
 static thread_local char g_err[512] = "";
 static unsigned long long g_launches = 0;
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char *e = getenv("TN_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 void count_launch() { __atomic_add_fetch(&g_launches, 1ull, __ATOMIC_RELAXED); }
 

@@ -120,6 +120,8 @@ __device__ __forceinline__ float act_small(const ActK &k, float z) {
 // smem: ws[(c*F+u)*F+v][4G] (taps flipped: true convolution) | bs[4G] | xs[NB][C][S][Sp] + guard
 template <int F>
 __global__ void __launch_bounds__(kST) small_fprop_kernel(const SmallArgs k) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   const int C = k.C, S = k.S, M = k.M, O = k.O, P = k.P, Pc = k.Pc, G = k.G, NB = k.NB, Sp = k.Sp;
   const int coP = 4 * G, SSp = S * Sp, CSSp = C * SSp, CSS = C * S * S, OO = O * O, PP = P * P;
@@ -356,6 +358,8 @@ __device__ __noinline__ void small_finish(const SmallArgs &k, float *red, float 
 
 template <int F>
 __global__ void __launch_bounds__(kST, 2) small_bwd_kernel(const __grid_constant__ SmallArgs k) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_flag;
   TN_PHASE(0);
@@ -675,6 +679,8 @@ __global__ void __launch_bounds__(kST, 2) small_bwd_kernel(const __grid_constant
 // smem: dbs[kST][4] | xs[NB][C][S][Sp] + guard (aliased by the slice sums at the end)
 template <int F>
 __global__ void __launch_bounds__(kST, 2) small_wgrad_kernel(const __grid_constant__ SmallArgs k) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(16) float sm[];
   __shared__ int s_flag;
   TN_PHASE(0);
@@ -967,7 +973,7 @@ int small_fprop(const float *x, const float *W, const float *bias, float *a, flo
   k.x = x; k.W = W; k.bias = bias; k.a = a; k.pooled = pooled; k.tie = tie;
   int rc = small_smem_attr(small_fprop_kernel<kSF>, pl.smem, who);
   if (rc) return rc;
-  small_fprop_kernel<kSF><<<pl.grid, pl.nt, pl.smem, st>>>(k);
+  launch_pdl(small_fprop_kernel<kSF>, dim3(pl.grid), dim3(pl.nt), pl.smem, st, k);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
 }
@@ -1048,13 +1054,13 @@ int small_bwd(const float *x, const float *a, const uint8_t *tie, const float *p
   if (direct) {
     int rc = small_smem_attr(small_wgrad_kernel<kSF>, pl.smem, who);
     if (rc) return rc;
-    small_wgrad_kernel<kSF><<<pl.grid, kST, pl.smem, st>>>(k);
+    launch_pdl(small_wgrad_kernel<kSF>, dim3(pl.grid), dim3(kST), pl.smem, st, k);
     TN_LAUNCH_CHECK(who);
     return TN_OK;
   }
   int rc = small_smem_attr(small_bwd_kernel<kSF>, pl.smem, who);
   if (rc) return rc;
-  small_bwd_kernel<kSF><<<pl.grid, kST, pl.smem, st>>>(k);
+  launch_pdl(small_bwd_kernel<kSF>, dim3(pl.grid), dim3(kST), pl.smem, st, k);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
 }

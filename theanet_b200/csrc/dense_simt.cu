@@ -225,6 +225,8 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(GemmArgs g) {
 // db[n] = sum_b g[b,n]; 32 columns x 32 row-slices per CTA, slices combined in a fixed order
 __global__ void __launch_bounds__(1024) colsum_kernel(const float *__restrict__ g,
                                                       float *__restrict__ db, int B, int N) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int n = blockIdx.x * 32 + tx;
@@ -337,7 +339,7 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
     cudaStream_t st = (cudaStream_t)stream;
     int rc = dense_tc_bwd_weights(x, gr, dW, B, n_in, n_out, tc_split(), st);
     if (rc) return rc;
-    colsum_kernel<<<ceil_div(n_out, 32), 1024, 0, st>>>(gr, db, B, n_out);
+    launch_pdl(colsum_kernel, dim3(ceil_div(n_out, 32)), dim3(1024), 0, st, gr, db, B, n_out);
     TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
     return TN_OK;
   }
@@ -349,7 +351,7 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
   cudaStream_t st = (cudaStream_t)stream;
   int rc = launch_gemm<1, 0, 2>(g, vec, "tn_dense_bwd_weights", st);
   if (rc) return rc;
-  colsum_kernel<<<ceil_div(n_out, 32), 1024, 0, st>>>(gr, db, B, n_out);
+  launch_pdl(colsum_kernel, dim3(ceil_div(n_out, 32)), dim3(1024), 0, st, gr, db, B, n_out);
   TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
   return TN_OK;
 }

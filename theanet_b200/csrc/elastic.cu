@@ -209,6 +209,8 @@ __global__ void elastic_warp_kernel(const float *__restrict__ corpus,
                                     const float *__restrict__ gfrac, int flip_on,
                                     uint32_t flip_thr, const float *__restrict__ flip_inj,
                                     uint64_t seed, float *__restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int hw = h * h;
   const int ngroups = (n + 3) >> 2;
   const int64_t total = (int64_t)B * ngroups;
@@ -316,9 +318,8 @@ extern "C" int tn_elastic_warp(const float *corpus, const int32_t *idx, const in
   const int blocks = (int)min64(ceil_div64(total, threads), (int64_t)kNumSM * 16);
   cudaStream_t st = (cudaStream_t)stream;
 #define TN_WARP_LAUNCH(MODE)                                                                  \
-  elastic_warp_kernel<MODE><<<blocks, threads, 0, st>>>(corpus, idx, ctl, B, n, h, invert,    \
-                                                        gidx, gfrac, flip_on, thr, flip_inj, \
-                                                        seed, out)
+  launch_pdl(elastic_warp_kernel<MODE>, dim3(blocks), dim3(threads), 0, st, corpus, idx, ctl, B, n, \
+             h, invert, gidx, gfrac, flip_on, thr, flip_inj, seed, out)
   if (mode == 0) TN_WARP_LAUNCH(0);
   else if (mode == 1) TN_WARP_LAUNCH(1);
   else TN_WARP_LAUNCH(2);

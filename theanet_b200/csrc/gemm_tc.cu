@@ -103,14 +103,47 @@ static __device__ __forceinline__ void tc_epi_quad_body(const TcArgs &g, int m, 
         if (n + j < g.N) mk[j] = g.mask_inj[(size_t)m * g.N + n + j];
     }
   }
+  // ReLU family (the shipped networks): selects on warp-uniform conditions instead of the
+  // per-element switch of the general path (its BSSY / BRXU chains cost ~700 cycles per quad)
+  const bool fam = g.ak.act == TN_ACT_LEAKY || g.ak.act == TN_ACT_LINEAR || g.ak.act == TN_ACT_RELU;
   if (g.epi == 0) {
+    if (fam) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float zz = v[j] + bq[j];
+        const float neg = g.ak.act == TN_ACT_LEAKY ? div100_rn(__fmul_rn(zz, g.ak.nn))
+                                                   : (g.ak.act == TN_ACT_LINEAR ? zz : 0.f);
+        const float a = zz > 0.f ? zz : neg;
+        v[j] = (a * mk[j]) * g.scale;      // mk = 1 without dropout, scale = 1 when training: exact
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + j < g.N) {
+          const float a = act_fwd_k(g.ak, v[j] + bq[j]);
+          v[j] = g.mask_on ? a * mk[j] : a;
+          if (g.scale != 1.f) v[j] *= g.scale;
+        }
+      }
+    }
+  } else if (g.epi == 1 && g.aux && fam) {
+    float ax[4] = {0.f, 0.f, 0.f, 0.f};
+    const float *ap = g.aux + (size_t)m * g.N + n;
+    if (n + 3 < g.N) {
+      const float4 a4 = *reinterpret_cast<const float4 *>(ap);
+      ax[0] = a4.x; ax[1] = a4.y; ax[2] = a4.z; ax[3] = a4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < g.N) ax[j] = ap[j];
+    }
+    const float s_pos = 1.f;
+    const float s_neg = g.ak.act == TN_ACT_LEAKY ? g.ak.s_neg : (g.ak.act == TN_ACT_LINEAR ? 1.f : 0.f);
+    const float s_zero = g.ak.act == TN_ACT_LEAKY ? g.ak.s_zero : (g.ak.act == TN_ACT_LINEAR ? 1.f : 0.f);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      if (n + j < g.N) {
-        const float a = act_fwd_k(g.ak, v[j] + bq[j]);
-        v[j] = g.mask_on ? a * mk[j] : a;
-        if (g.scale != 1.f) v[j] *= g.scale;
-      }
+      const float d = ax[j] > 0.f ? s_pos : (ax[j] < 0.f ? s_neg : s_zero);
+      v[j] = (v[j] * mk[j]) * d;
     }
   } else if (g.epi == 1 && g.aux) {
     float ax[4] = {0.f, 0.f, 0.f, 0.f};
@@ -159,6 +192,11 @@ static __device__ __noinline__ void tc_epi_quad(const TcArgs &g, int m, int n, f
                                                 float v2, float v3, uint32_t step,
                                                 uint32_t sample0) {
   tc_epi_quad_body(g, m, n, v0, v1, v2, v3, tc_bias_quad(g, n), step, sample0);
+}
+// the same with the bias quad already in registers (cluster kernel: one quad column per thread)
+static __device__ __noinline__ void tc_epi_quad_b(const TcArgs &g, int m, int n, float4 v, float4 b4,
+                                                  uint32_t step, uint32_t sample0) {
+  tc_epi_quad_body(g, m, n, v.x, v.y, v.z, v.w, b4, step, sample0);
 }
 
 template <int BN, int SPLIT>
@@ -414,7 +452,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // from every peer's shared memory over DSMEM (ld.shared::cluster), adds them in split order with
 // round-to-nearest float adds -- deterministic -- and runs the fused epilogue with coalesced
 // float4 stores.  No workspace in HBM, no tickets, no serial last-CTA tail; wide tiles and one wave
-// of CTAs whatever the shape.
+// of CTAs whatever the shape.  (Pushing rows to their owners with st.shared::cluster instead was
+// slower: a thread's TMEM row scatters 16-byte stores over the SM-to-SM network.)
 //   warps 0..3 : TMA producers (k-blocks round-robin)        warp 8 : MMA issuer + TMEM owner
 //   warps 4..7 : lo = x - hi transform of every landed stage, then the TMEM drain
 //   all warps  : the cross-CTA reduction + epilogue of the CTA's row slice
@@ -462,6 +501,50 @@ __device__ __forceinline__ float4 ld_cluster_f4(uint32_t addr) {
     if (g.dbg) g.dbg[(size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (i)] = clock64(); \
   } while (0)
 
+// Cross-CTA reduction + epilogue of one row slice (see the kernel): NSMAX >= ns peers, IB items
+// per pass with all their DSMEM loads issued before the first add.
+template <int BN, int NSMAX, int IB>
+static __device__ __forceinline__ void sk_reduce(const TcArgs &g, uint32_t base, int ns, int z,
+                                                 int r0, int items, int m0, int eq, int en,
+                                                 float4 ebias, uint32_t step, uint32_t sample0) {
+  constexpr int QPR = BN / 4;
+  uint32_t peer[NSMAX];
+#pragma unroll
+  for (int sp = 0; sp < NSMAX; ++sp) peer[sp] = cluster_map(base, (uint32_t)min(sp, ns - 1));
+#pragma unroll 1
+  for (int it0 = threadIdx.x; it0 < items; it0 += IB * TC_THREADS) {
+    float4 v[IB][NSMAX];
+#pragma unroll
+    for (int b = 0; b < IB; ++b) {
+      const int it = it0 + b * TC_THREADS;
+      const int r = r0 + it / QPR;
+      const uint32_t off = (uint32_t)r * (BN * 4) + 16u * ((uint32_t)eq ^ ((uint32_t)r & (QPR - 1)));
+#pragma unroll
+      for (int sp = 0; sp < NSMAX; ++sp)
+        if (sp < ns && it < items) {
+          if (sp == z) {     // this CTA's own partial: plain shared-memory load, not the SM-to-SM path
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(v[b][sp].x), "=f"(v[b][sp].y), "=f"(v[b][sp].z), "=f"(v[b][sp].w)
+                         : "r"(base + off)
+                         : "memory");
+          } else {
+            v[b][sp] = ld_cluster_f4(peer[sp] + off);
+          }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < IB; ++b) {
+      const int it = it0 + b * TC_THREADS;
+      if (it >= items) break;
+      float4 sum = v[b][0];
+#pragma unroll
+      for (int sp = 1; sp < NSMAX; ++sp)
+        if (sp < ns) { sum.x += v[b][sp].x; sum.y += v[b][sp].y; sum.z += v[b][sp].z; sum.w += v[b][sp].w; }
+      if (en < g.N) tc_epi_quad_b(g, m0 + r0 + it / QPR, en, sum, ebias, step, sample0);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -490,8 +573,8 @@ gemm_tc_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const int kb0 = (int)(((long long)z * nkb_all) / ns);
   const int nkb = (int)(((long long)(z + 1) * nkb_all) / ns) - kb0;   // >= 1 (host: ns <= nkb_all)
 
+  pdl_trigger();
   if (threadIdx.x == 0) {
-    TN_GSTAMP(0);
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
     for (int s = 0; s < S; ++s) {
@@ -508,7 +591,11 @@ gemm_tc_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   tcgen05_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
-  if (threadIdx.x == 0) TN_GSTAMP(1);
+  pdl_wait();       // barriers, TMEM and descriptors are set up; global memory from here on
+  if (threadIdx.x == 0) {
+    TN_GSTAMP(0);
+    TN_GSTAMP(1);
+  }
   // epilogue operands of this thread's quad column, fetched while the pipeline fills
   static_assert(TC_THREADS % QPR == 0, "a thread keeps one quad column in the reduction");
   const int eq = threadIdx.x % QPR, en = n0 + 4 * eq;
@@ -583,8 +670,6 @@ gemm_tc_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else {
     // ===== lo = x - hi of every landed stage (the raw tile is the hi operand), then the drain =====
     const int et = threadIdx.x - 32 * TC_PROD;
-    const int q = warp & 3;
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S;
       const uint32_t ph = (uint32_t)(kb / S) & 1u;
@@ -616,6 +701,8 @@ gemm_tc_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // row (q*32 + lane) of the partial tile -> this CTA's shared memory (the stage ring is idle:
     // every load has landed and every MMA has completed), quads XOR-swizzled by the row so that a
     // warp's 32 rows hit different banks
+    const int q = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const int row = q * 32 + lane;
     const uint32_t prow = base + (uint32_t)row * (BN * 4);
 #pragma unroll 1
@@ -647,41 +734,18 @@ gemm_tc_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 
-  // ---- this CTA's row slice: add the ns partials in split order + fused epilogue ------------
-  // item = (row, quad) with the quad index fastest: TC_THREADS is a multiple of QPR, so a thread
-  // keeps ONE quad column for all its items (bias quad in registers, loaded before the main loop).
-  // Two items per pass, all their DSMEM loads in flight before the first add.
+  // ---- this CTA's row slice: add the ns partials in split order (fixed: deterministic) + fused
+  // epilogue.  item = (row, quad), quad fastest: TC_THREADS is a multiple of QPR, so a thread keeps
+  // ONE quad column (its bias quad is already in registers).  A DSMEM load takes ~1000 cycles
+  // under load: all the loads of up to 4 items (<= 16 float4) are in flight before the first add.
   const int rps = (TC_BM + ns - 1) / ns;           // rows per slice
   const int r0 = z * rps;
   const int r1 = min(min(r0 + rps, TC_BM), g.M - m0);
   const int items = max(r1 - r0, 0) * QPR;
-  uint32_t peer[SK_MAX_SPLIT];
-#pragma unroll
-  for (int sp = 0; sp < SK_MAX_SPLIT; ++sp) peer[sp] = cluster_map(base, (uint32_t)min(sp, ns - 1));
-  constexpr int IB = 2;
-  for (int it0 = threadIdx.x; it0 < items; it0 += IB * TC_THREADS) {
-    float4 v[IB][SK_MAX_SPLIT];
-#pragma unroll
-    for (int b = 0; b < IB; ++b) {
-      const int it = it0 + b * TC_THREADS;
-      const int r = r0 + it / QPR;
-      const uint32_t off = (uint32_t)r * (BN * 4) + 16u * ((uint32_t)eq ^ ((uint32_t)r & (QPR - 1)));
-#pragma unroll
-      for (int sp = 0; sp < SK_MAX_SPLIT; ++sp)
-        if (sp < ns && it < items) v[b][sp] = ld_cluster_f4(peer[sp] + off);
-    }
-#pragma unroll
-    for (int b = 0; b < IB; ++b) {
-      const int it = it0 + b * TC_THREADS;
-      if (it >= items) break;
-      float4 sum = v[b][0];
-#pragma unroll
-      for (int sp = 1; sp < SK_MAX_SPLIT; ++sp)
-        if (sp < ns) { sum.x += v[b][sp].x; sum.y += v[b][sp].y; sum.z += v[b][sp].z; sum.w += v[b][sp].w; }
-      if (en < g.N)
-        tc_epi_quad_body(g, m0 + r0 + it / QPR, en, sum.x, sum.y, sum.z, sum.w, ebias, step, sample0);
-    }
-  }
+  if (ns <= 4)
+    sk_reduce<BN, 4, 4>(g, base, ns, z, r0, items, m0, eq, en, ebias, step, sample0);
+  else
+    sk_reduce<BN, 8, 2>(g, base, ns, z, r0, items, m0, eq, en, ebias, step, sample0);
   if (threadIdx.x == 0) TN_GSTAMP(7);
   cluster_sync_all();                      // nobody leaves while a peer may still read its tile
 }
@@ -848,13 +912,15 @@ static int launch_sk(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArg
   cfg.blockDim = dim3(TC_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 1;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = ns;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   e = cudaLaunchKernelEx(&cfg, k, tmA, tmB, g);
   TN_REQUIRE(e == cudaSuccess, TN_ERR_CUDA, "%s: %s", who, cudaGetErrorString(e));
   TN_LAUNCH_CHECK(who);

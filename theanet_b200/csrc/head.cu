@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(256) softmax_head_kernel(const HeadArgs a) {
   constexpr int LDK = NQ * 128;
   float *ws = sm;              // [n_out][LDK], zero padded
   float *bs = sm + NP * LDK;   // [NP]
+  pdl_trigger();
+  pdl_wait();
   for (int t = threadIdx.x; t < a.n_out * LDK; t += blockDim.x) {
     const int j = t / LDK, k = t % LDK;
     ws[t] = k < a.n_in ? a.W[(size_t)k * a.n_out + j] : 0.f;
@@ -182,6 +184,8 @@ head_dw_kernel(const float *__restrict__ h, const float *__restrict__ g, float *
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int tile = blockIdx.x, chunk = blockIdx.y, nchunks = gridDim.y;
   const int i = tile * 32 + lane;
+  pdl_trigger();
+  pdl_wait();
   float *part_w = ws_f;
   float *part_b = ws_f + (size_t)nchunks * n_in * n_out;
   int *tickets = reinterpret_cast<int *>(part_b + (size_t)nchunks * n_out);
@@ -275,7 +279,7 @@ static int launch_head(const HeadArgs &a, cudaStream_t st) {
   int rc = head_smem(softmax_head_kernel<NP, NQ>, smem, who);
   if (rc) return rc;
   const int blocks = min(ceil_div(a.B, 8), kNumSM);
-  softmax_head_kernel<NP, NQ><<<blocks, 256, smem, st>>>(a);
+  launch_pdl(softmax_head_kernel<NP, NQ>, dim3(blocks), dim3(256), smem, st, a);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
 }
@@ -341,10 +345,10 @@ extern "C" int tn_softmax_head_bwd_weights(const float *h, const float *g, float
   dim3 grid(ceil_div(n_in, 32), ceil_div(B, kHeadChunk));
   cudaStream_t st = (cudaStream_t)stream;
   float *ws = (float *)workspace;
-  if (n_out <= 8) head_dw_kernel<8><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
-  else if (n_out <= 12) head_dw_kernel<12><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
-  else if (n_out <= 16) head_dw_kernel<16><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
-  else head_dw_kernel<32><<<grid, 256, 0, st>>>(h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  if (n_out <= 8) launch_pdl(head_dw_kernel<8>, grid, dim3(256), 0, st, h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  else if (n_out <= 12) launch_pdl(head_dw_kernel<12>, grid, dim3(256), 0, st, h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  else if (n_out <= 16) launch_pdl(head_dw_kernel<16>, grid, dim3(256), 0, st, h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
+  else launch_pdl(head_dw_kernel<32>, grid, dim3(256), 0, st, h, g, dW, db, ws, B, n_in, n_out, rowloss, nll_sum);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
 }

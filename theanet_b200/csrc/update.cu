@@ -51,6 +51,8 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
                 float grad_scale, float *__restrict__ wt_partial, int *ticket,
                 const float *__restrict__ nll_sum, float nll_scale, float *__restrict__ cost_out,
                 const __grid_constant__ PeerArgs peers, int64_t nll_slot) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[kUpdThreads / 32];
   __shared__ float red2[kUpdThreads];
   __shared__ int s_last;
@@ -270,9 +272,8 @@ static int update_impl(float *theta, float *vel, const float *grad, const tn_par
   cudaStream_t st = (cudaStream_t)stream;
   float *wt_partial = (float *)workspace;
   int *ticket = reinterpret_cast<int *>(wt_partial + (total / kUpdPerBlock + nseg + 1));
-  sgd_step_kernel<<<(unsigned)nb, kUpdThreads, 0, st>>>(theta, vel, grad, tab, ctl, grad_scale,
-                                                        wt_partial, ticket, nll_sum, nll_scale,
-                                                        cost_out, peers, total);
+  launch_pdl(sgd_step_kernel, dim3((unsigned)nb), dim3(kUpdThreads), 0, st, theta, vel, grad, tab, ctl,
+             grad_scale, wt_partial, ticket, nll_sum, nll_scale, cost_out, peers, total);
   TN_LAUNCH_CHECK("tn_sgd_momentum_maxnorm_update(step)");
   for (int s = 0; s < nseg; ++s) {
     const tn_param_seg &sg = segs[s];
