@@ -280,6 +280,16 @@ int tn_dense_bwd_data(const float *g, const float *W, float *dx, int B, int n_in
 /* dW = x^T.g, db = column sums of g */
 int tn_dense_bwd_weights(const float *x, const float *g, float *dW, float *db, int B, int n_in,
                          int n_out, void *stream);
+/* The same two products with a bound on the SMs (= CTAs of the cluster split-K tensor-core kernel)
+ * each may occupy, 0 = all: the two gradients of a dense layer are independent, and a caller that
+ * launches them on two streams with max_sms summing to <= 148 gets them side by side instead of
+ * two kernels that each want the whole GPU and take turns (NeuralNet: 1/3 for dW, 2/3 for dX). */
+int tn_dense_bwd_data_sm(const float *g, const float *W, float *dx, int B, int n_in, int n_out,
+                         const float *prev_out, int act_prev, int nn_prev, double pkeep_prev,
+                         uint64_t seed_prev, const int32_t *ctl, const float *mask_inj_prev,
+                         int max_sms, void *stream);
+int tn_dense_bwd_weights_sm(const float *x, const float *g, float *dW, float *db, int B, int n_in,
+                            int n_out, int max_sms, void *stream);
 /* Dense-path selector (process-wide debugging / benchmarking knob): 0 = auto (tcgen05 tensor cores
  * with 3xTF32 error compensation whenever n_in, n_out are multiples of 4 and n_out > 32, CUDA-core
  * kernels otherwise; the K range of a product is split over a thread-block cluster whose CTAs
@@ -381,7 +391,8 @@ int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
                                    void *stream);
 /* Data parallel, fused: the same update with the gradient all-reduce folded in.  peer_grads[r] /
  * peer_flags[r] (host arrays of `world` device pointers) are rank r's flat gradient buffer
- * (total + 4 floats; [total] is its NLL partial sum) and flag array (int[8], zero-filled once),
+ * (total + 4 floats; [total] is its NLL partial sum) and flag array (int[16], zero-filled once:
+ * words 0..7 receive the ranks' tokens, word 8 counts this rank's executions of the kernel),
  * mapped into this process with tn_ipc_open_handle (entry [rank] is the local buffer).  The kernel
  * signals and waits for all ranks, sums the buffers in rank order while it updates, and needs the
  * caller to alternate between two gradient buffers from step to step (see update.cu). */

@@ -320,6 +320,43 @@ def test_cifar3conv_bf16_tensor_core_stack_matches_oracle():
     assert abs(e - oe) < 1e-6 and abs(pr - opr) <= TOL_BF16 * opr
 
 
+BF16_NO_POOL = {
+    'hidden': [('ConvLayer', {'num_maps': 64, 'filter_sz': 3, 'stride': 1, 'mode': 'same', 'actvn': 'relu50'}),
+               ('HiddenLayer', {'n_out': 64, 'pdrop': .25, 'actvn': 'relu10'})],
+    'dropout': [('ConvLayer', {'num_maps': 64, 'filter_sz': 3, 'stride': 1, 'mode': 'same', 'actvn': 'relu50'}),
+                ('DropOutLayer', {'pdrop': .3}),
+                ('HiddenLayer', {'n_out': 64, 'pdrop': 0, 'actvn': 'relu10'})],
+}
+
+
+@pytest.mark.parametrize('case', sorted(BF16_NO_POOL))
+def test_bf16_conv_without_pool_feeding_float32_consumers(case):
+    """A tensor-core ConvLayer with a leaky reluNN and NO PoolLayer above it, feeding a HiddenLayer /
+    a DropOutLayer: its act' must be applied exactly once (by the conv branch of the backward pass,
+    not again by the consumer's fused epilogue -- the negative-side slope would come out squared)."""
+    from theanet_b200.neuralnet import NeuralNet
+    B = 8
+    layers = [('InputLayer', {'img_sz': 8, 'num_maps': 64})] + BF16_NO_POOL[case] + \
+        [('SoftmaxLayer', {'n_out': 10})]
+    tp = {'BATCH_SZ': B, 'NUM_EPOCHS': 1, 'EPOCHS_TO_TEST': 1, 'TEST_SAMP_SZ': B, 'INIT_LEARNING_RATE': .05,
+          'EPOCHS_TO_HALF_RATE': 2, 'SEED': 99, 'CONV_DTYPE': 'bfloat16'}
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((2 * B, 64, 8, 8)).astype(np.float32)        # half of the pre-activations < 0
+    y = rng.integers(0, 10, 2 * B).astype(np.int32)
+    net = NeuralNet(copy.deepcopy(layers), dict(tp))
+    assert sorted(net.conv_tc) == [1] and net.conv_tc[1].pool is None
+    on = O.OracleNet(copy.deepcopy(layers), dict(tp))
+    fn = net.get_trin_model(x, y)
+    for s in range(2):
+        cost, _, lp = fn(s)
+        ocost, olp = on.train_step(x[s * B:(s + 1) * B], y[s * B:(s + 1) * B], step=s, sample0=0)
+        assert abs(cost - ocost) <= TOL_BF16 * abs(ocost), (s, cost, ocost)
+        for li, (gg, og) in enumerate(zip(net.get_gradients(), on.last_grads)):
+            for k, u in enumerate(gg):
+                assert rel2(u, og[k]) < TOL_BF16, 'step {} grad layer {} tensor {}: {}'.format(
+                    s, li, k, rel2(u, og[k]))
+
+
 @pytest.mark.parametrize('use_graph', [True, False])
 def test_exact_resume_with_momentum_step_and_stream_seeds(tmp_path, use_graph):
     """The reference's .pkl carries weights only: a resumed run starts with zero momentum and new

@@ -82,6 +82,8 @@ SIGNATURES = {
     'tn_dense_fwd': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _D, _U64, _P, _P, _F, _P]),
     'tn_dense_bwd_data': (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _D, _U64, _P, _P, _P]),
     'tn_dense_bwd_weights': (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    'tn_dense_bwd_data_sm': (_I, [_P, _P, _P, _I, _I, _I, _P, _I, _I, _D, _U64, _P, _P, _I, _P]),
+    'tn_dense_bwd_weights_sm': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     'tn_set_dense_mode': (_I, [_I]),
     'tn_dense_debug_timestamps': (_I, [_P]),
     'tn_subsample2d': (_I, [_P, _P, _I, _I, _I, _I, _P]),

@@ -285,7 +285,7 @@ extern "C" int tn_dense_fwd(const float *x, const float *W, const float *bias, f
   if (use_tc(n_in, n_out, x, W, out))
     return dense_tc_fwd(x, W, bias, out, B, n_in, n_out, act, (float)act_nn,
                         mask_mode(pkeep, mask_inj), bernoulli_threshold(pkeep), seed, ctl,
-                        mask_inj, out_scale, tc_split(), (cudaStream_t)stream);
+                        mask_inj, out_scale, tc_split(), 0, (cudaStream_t)stream);
   GemmArgs g{};
   g.A = x; g.B = W; g.C = out;
   g.M = B; g.N = n_out; g.K = n_in; g.lda = n_in; g.ldb = n_out; g.ldc = n_out;
@@ -297,10 +297,10 @@ extern "C" int tn_dense_fwd(const float *x, const float *W, const float *bias, f
   return launch_gemm<0, 0, 0>(g, vec, "tn_dense_fwd", (cudaStream_t)stream);
 }
 
-extern "C" int tn_dense_bwd_data(const float *gr, const float *W, float *dx, int B, int n_in,
-                                 int n_out, const float *prev_out, int act_prev, int nn_prev,
-                                 double pkeep_prev, uint64_t seed_prev, const int32_t *ctl,
-                                 const float *mask_inj_prev, void *stream) {
+extern "C" int tn_dense_bwd_data_sm(const float *gr, const float *W, float *dx, int B, int n_in,
+                                    int n_out, const float *prev_out, int act_prev, int nn_prev,
+                                    double pkeep_prev, uint64_t seed_prev, const int32_t *ctl,
+                                    const float *mask_inj_prev, int max_sms, void *stream) {
   TN_REQUIRE(gr && W && dx, TN_ERR_ARG, "tn_dense_bwd_data: null argument");
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0, TN_ERR_SHAPE, "tn_dense_bwd_data: bad shape");
   if (dense_small_ok(n_in, n_out)) {
@@ -315,7 +315,7 @@ extern "C" int tn_dense_bwd_data(const float *gr, const float *W, float *dx, int
     TN_REQUIRE(mo != 1 || ctl, TN_ERR_ARG, "tn_dense_bwd_data: dropout needs ctl");
     return dense_tc_bwd_data(gr, W, dx, B, n_in, n_out, prev_out, act_prev, (float)nn_prev, mo,
                              bernoulli_threshold(pkeep_prev), seed_prev, ctl, mask_inj_prev,
-                             tc_split(), (cudaStream_t)stream);
+                             tc_split(), max_sms, (cudaStream_t)stream);
   }
   GemmArgs g{};
   g.A = gr; g.B = W; g.C = dx;
@@ -329,15 +329,23 @@ extern "C" int tn_dense_bwd_data(const float *gr, const float *W, float *dx, int
   return launch_gemm<0, 1, 1>(g, vec, "tn_dense_bwd_data", (cudaStream_t)stream);
 }
 
-extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, float *db, int B,
-                                    int n_in, int n_out, void *stream) {
+extern "C" int tn_dense_bwd_data(const float *gr, const float *W, float *dx, int B, int n_in,
+                                 int n_out, const float *prev_out, int act_prev, int nn_prev,
+                                 double pkeep_prev, uint64_t seed_prev, const int32_t *ctl,
+                                 const float *mask_inj_prev, void *stream) {
+  return tn_dense_bwd_data_sm(gr, W, dx, B, n_in, n_out, prev_out, act_prev, nn_prev, pkeep_prev,
+                              seed_prev, ctl, mask_inj_prev, 0, stream);
+}
+
+extern "C" int tn_dense_bwd_weights_sm(const float *x, const float *gr, float *dW, float *db, int B,
+                                       int n_in, int n_out, int max_sms, void *stream) {
   TN_REQUIRE(x && gr && dW && db, TN_ERR_ARG, "tn_dense_bwd_weights: null argument");
   TN_REQUIRE(B > 0 && n_in > 0 && n_out > 0, TN_ERR_SHAPE, "tn_dense_bwd_weights: bad shape");
   if (dense_small_ok(n_in, n_out))
     return dense_bwd_weights_small(x, gr, dW, db, B, n_in, n_out, (cudaStream_t)stream);
   if (use_tc(n_in, n_out, x, gr, dW)) {
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = dense_tc_bwd_weights(x, gr, dW, B, n_in, n_out, tc_split(), st);
+    int rc = dense_tc_bwd_weights(x, gr, dW, B, n_in, n_out, tc_split(), max_sms, st);
     if (rc) return rc;
     launch_pdl(colsum_kernel, dim3(ceil_div(n_out, 32)), dim3(1024), 0, st, gr, db, B, n_out);
     TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
@@ -354,6 +362,11 @@ extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, 
   launch_pdl(colsum_kernel, dim3(ceil_div(n_out, 32)), dim3(1024), 0, st, gr, db, B, n_out);
   TN_LAUNCH_CHECK("tn_dense_bwd_weights(db)");
   return TN_OK;
+}
+
+extern "C" int tn_dense_bwd_weights(const float *x, const float *gr, float *dW, float *db, int B,
+                                    int n_in, int n_out, void *stream) {
+  return tn_dense_bwd_weights_sm(x, gr, dW, db, B, n_in, n_out, 0, stream);
 }
 
 // Debug aid (tools/gemm_phase_times.py): when buf != NULL, every CTA of the cluster split-K kernel

@@ -880,14 +880,15 @@ static int sk_max_clusters(int ns) {
 
 // one wave of CTAs: tiles x splits ~ number of SMs, at least two k-blocks per split, the cluster
 // small enough that every tile's cluster is co-resident
-static SkPlan sk_plan(int M, int N, int K) {
+static SkPlan sk_plan(int M, int N, int K, int max_sms) {
   SkPlan p;
   p.BN = N > 64 ? 128 : 64;
   const int fb = sk_env("TN_SK_BN", 0);
   if (fb == 64 || fb == 128) p.BN = fb;
   p.tiles = ceil_div(M, TC_BM) * ceil_div(N, p.BN);
   const int nkb = ceil_div(K, SK_BK);
-  int ns = std::max(1, kNumSM / p.tiles);
+  const int sms = max_sms > 0 ? std::min(max_sms, kNumSM) : kNumSM;
+  int ns = std::max(1, sms / p.tiles);
   ns = std::min(ns, std::max(1, nkb / 2));
   ns = std::min(ns, SK_MAX_SPLIT);
   const int fs = sk_env("TN_SK_SPLIT", 0);
@@ -929,8 +930,8 @@ static int launch_sk(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcArg
 
 // same contract as gemm_tc()
 static int gemm_tc_sk(const float *A, int lda, int a_mn, const float *B, int ldb, int b_mn, TcArgs g,
-                      const char *who, cudaStream_t st) {
-  const SkPlan p = sk_plan(g.M, g.N, g.K);
+                      int max_sms, const char *who, cudaStream_t st) {
+  const SkPlan p = sk_plan(g.M, g.N, g.K, max_sms);
   CUtensorMap tmA, tmB;
   int rc;
   if (!a_mn) rc = tc_make_map_2d(&tmA, A, g.M, g.K, lda, 32, TC_BM, 0, who);
@@ -959,37 +960,39 @@ bool dense_tc_ok(int n_in, int n_out, const void *p0, const void *p1, const void
 
 int dense_tc_fwd(const float *x, const float *W, const float *bias, float *out, int B, int n_in,
                  int n_out, int act, float act_nn, int mask_on, uint32_t thr, uint64_t seed,
-                 const int32_t *ctl, const float *mask_inj, float scale, int split,
+                 const int32_t *ctl, const float *mask_inj, float scale, int split, int max_sms,
                  cudaStream_t st) {
   TcArgs g{};
   g.C = out; g.ldc = n_out; g.M = B; g.N = n_out; g.K = n_in;
   g.epi = 0; g.bias = bias; g.mask_inj = mask_inj; g.ctl = ctl; g.seed = seed; g.thr = thr;
   g.mask_on = mask_on; g.ak = make_actk(act, (int)act_nn); g.scale = scale;
   // A = x (B x n_in, K contiguous); B[n][k] = W[k][n] (N contiguous)
-  if (split == 1) return gemm_tc_sk(x, n_in, 0, W, n_out, 1, g, "tn_dense_fwd(tc,split-K)", st);
+  if (split == 1) return gemm_tc_sk(x, n_in, 0, W, n_out, 1, g, max_sms, "tn_dense_fwd(tc,split-K)", st);
   return gemm_tc(x, n_in, 0, W, n_out, 1, g, split, "tn_dense_fwd(tc)", st);
 }
 
 int dense_tc_bwd_data(const float *gr, const float *W, float *dx, int B, int n_in, int n_out,
                       const float *prev_out, int act, float act_nn, int mask_on, uint32_t thr,
                       uint64_t seed, const int32_t *ctl, const float *mask_inj, int split,
-                      cudaStream_t st) {
+                      int max_sms, cudaStream_t st) {
   TcArgs g{};
   g.C = dx; g.ldc = n_in; g.M = B; g.N = n_in; g.K = n_out;
   g.epi = 1; g.aux = prev_out; g.mask_inj = mask_inj; g.ctl = ctl; g.seed = seed; g.thr = thr;
   g.mask_on = mask_on; g.ak = make_actk(act, (int)act_nn); g.scale = 1.f;
   // A = g (B x n_out, K contiguous); B[n][k] = W[n][k] (K contiguous)
-  if (split == 1) return gemm_tc_sk(gr, n_out, 0, W, n_out, 0, g, "tn_dense_bwd_data(tc,split-K)", st);
+  if (split == 1)
+    return gemm_tc_sk(gr, n_out, 0, W, n_out, 0, g, max_sms, "tn_dense_bwd_data(tc,split-K)", st);
   return gemm_tc(gr, n_out, 0, W, n_out, 0, g, split, "tn_dense_bwd_data(tc)", st);
 }
 
 int dense_tc_bwd_weights(const float *x, const float *gr, float *dW, int B, int n_in, int n_out,
-                         int split, cudaStream_t st) {
+                         int split, int max_sms, cudaStream_t st) {
   TcArgs g{};
   g.C = dW; g.ldc = n_out; g.M = n_in; g.N = n_out; g.K = B;
   g.epi = 2; g.scale = 1.f; g.ak = make_actk(TN_ACT_LINEAR, 0);
   // A[m][k] = x[k][m] (M contiguous); B[n][k] = g[k][n] (N contiguous)
-  if (split == 1) return gemm_tc_sk(x, n_in, 1, gr, n_out, 1, g, "tn_dense_bwd_weights(tc,split-K)", st);
+  if (split == 1)
+    return gemm_tc_sk(x, n_in, 1, gr, n_out, 1, g, max_sms, "tn_dense_bwd_weights(tc,split-K)", st);
   return gemm_tc(x, n_in, 1, gr, n_out, 1, g, split, "tn_dense_bwd_weights(tc)", st);
 }
 

@@ -19,14 +19,19 @@ constexpr int kUpdPerBlock = kUpdThreads * 4;
 // memory) and adds them in rank order -- the same order everywhere, so the replicas stay bit
 // identical -- inside the optimiser kernel itself.  Handshake: each rank stores a step token into
 // every peer's flag array when its own gradients are complete (it is the first thing this kernel
-// does, after all backward kernels in stream order) and spins until all tokens have arrived.
+// does, after all backward kernels in stream order) and spins until all tokens have arrived.  The
+// token is a per-rank EXECUTION counter kept on the device (word kMaxPeers of the rank's own flag
+// array, advanced by the last CTA of every execution): ranks run the kernel in lockstep, so their
+// counters agree, and re-running a step (graph warm-up followed by its replay, a resumed run that
+// rewinds the step counter) can never find last time's token already in place.
 // Gradient buffers are double-buffered by step parity, which makes the "peers are done reading"
 // direction implicit: a buffer is rewritten two steps later, after its owner has passed the next
 // step's handshake, which every reader only enters once it has finished this step's reads.
 constexpr int kMaxPeers = 8;
 struct PeerArgs {
   const float *grad[kMaxPeers];   // grad[r]: rank r's gradient buffer of this parity (r == rank: local)
-  int *flags[kMaxPeers];          // flags[r]: rank r's flag array (int[kMaxPeers]); [rank] is local
+  int *flags[kMaxPeers];          // flags[r]: rank r's flag array (int[2*kMaxPeers]); [rank] is local:
+                                  // words 0..7 tokens by source rank, word 8 the execution counter
   int world, rank;
 };
 
@@ -57,8 +62,9 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   __shared__ float red2[kUpdThreads];
   __shared__ int s_last;
   const int W = peers.world;
+  int token = 0;
   if (W > 1) {
-    const int token = ctl[TN_CTL_STEP] + 1;
+    token = __ldcg(peers.flags[peers.rank] + kMaxPeers) + 1;
     if (blockIdx.x == 0 && threadIdx.x < W) {
       __threadfence_system();
       st_release_sys(peers.flags[threadIdx.x] + peers.rank, token);   // "my gradients are complete"
@@ -136,7 +142,7 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
     for (int w = 0; w < kUpdThreads / 32; ++w) t += red[w];
     wt_partial[blockIdx.x] = t;
   }
-  if (!cost_out) return;
+  if (!cost_out && W <= 1) return;
   // the last CTA to finish (ticket) adds the per-CTA weight-cost partials in a fixed order:
   // cost = nll * nll_scale + L1/L2 cost of the PRE-update theta  (no second launch)
   __threadfence();
@@ -149,6 +155,9 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // every CTA has read the execution counter (they all passed the ticket): advance it
+  if (W > 1 && threadIdx.x == 0) peers.flags[peers.rank][kMaxPeers] = token;
+  if (!cost_out) return;
   float csum = 0.f;
   for (int i = threadIdx.x; i < (int)gridDim.x; i += kUpdThreads) csum += __ldcg(wt_partial + i);
   red2[threadIdx.x] = csum;

@@ -24,6 +24,10 @@ class DistContext:
         if self.world > 1:
             dist.broadcast(t, src=src, group=self.group)
 
+    def barrier(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
 
 def shard_bounds(batch_index, global_batch, rank, world):
     """Rows [lo, hi) of the corpus that `rank` processes for minibatch `batch_index`."""
@@ -78,9 +82,9 @@ class PeerBuffers:
             _C.call('tn_ipc_get_handle', ptr, buf)
             return buf.raw
 
-        own = [alloc(4 * nfloats), alloc(4 * nfloats), alloc(4 * 8)]
+        own = [alloc(4 * nfloats), alloc(4 * nfloats), alloc(4 * 16)]   # flags: 8 tokens + the epoch word
         self.grad = [torch.as_tensor(_RawCuda(own[k], nfloats, '<f4'), device=device) for k in (0, 1)]
-        self.flags = torch.as_tensor(_RawCuda(own[2], 8, '<i4'), device=device)
+        self.flags = torch.as_tensor(_RawCuda(own[2], 16, '<i4'), device=device)
         torch.cuda.synchronize(device)
         mine = [handle(p) for p in own]
         everyone = [None] * W

@@ -116,6 +116,8 @@ class NeuralNet():
         self.fuse_head = fuse_head
         self.nccl_in_graph = os.environ.get('TN_GRAPH_NCCL', '0') == '1'
         self.overlap_wgrad = os.environ.get('TN_OVERLAP_WGRAD', '1') == '1'
+        self.sm_count = (torch.cuda.get_device_properties(self.device).multi_processor_count
+                         if self.device.type == 'cuda' else 148)
         self._side = None
 
         # Input Layer
@@ -698,6 +700,11 @@ class NeuralNet():
             pk = 1. - lyr.pdrop if lyr.pdrop else 1.0
             return (self.out[li], lyr.act.code, lyr.act.nn, pk, lyr.seed or 0, self._inj(li, 'mask'))
         if isinstance(lyr, ConvLayer):
+            if li in self.conv_tc:
+                # the bf16 tensor-core branch of _backward applies act' itself
+                # (tn_poolbwd_nhwc_bf16 gets the layer's activation): a consumer that fused it as
+                # well would square the negative-side slope of a leaky reluNN
+                return None
             return (self.out[li], lyr.act.code, lyr.act.nn, 1.0, 0, None)
         return None
 
@@ -756,14 +763,19 @@ class NeuralNet():
             elif isinstance(lyr, HiddenLayer):
                 if self.trainable[li] and isinstance(lyr, SoftAuxLayer):
                     self._aux_backward(lyr, g, st)
+                # the two gradients are independent: when both are needed (and may overlap) they get
+                # 1/3 and 2/3 of the SMs so that they run side by side instead of taking turns
+                share = bool(self.trainable[li] and below and self.overlap_wgrad)
                 if self.trainable[li]:
                     with self._wgrad_stream() as sw:
-                        _C.call('tn_dense_bwd_weights', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
-                                _C.ptr(lyr.b.grad), B, lyr.n_in, lyr.n_out, sw)
+                        _C.call('tn_dense_bwd_weights_sm', _C.ptr(x), _C.ptr(g), _C.ptr(lyr.w.grad),
+                                _C.ptr(lyr.b.grad), B, lyr.n_in, lyr.n_out,
+                                self.sm_count // 3 if share else 0, sw)
                 if below:
                     po, ac, nn, pk, sd, mi = fuse or (None, 0, 0, 1.0, 0, None)
-                    _C.call('tn_dense_bwd_data', _C.ptr(g), _C.ptr(lyr.w.tensor), _C.ptr(dx), B,
-                            lyr.n_in, lyr.n_out, _C.ptr(po), ac, nn, pk, sd, ctl, mi, st)
+                    _C.call('tn_dense_bwd_data_sm', _C.ptr(g), _C.ptr(lyr.w.tensor), _C.ptr(dx), B,
+                            lyr.n_in, lyr.n_out, _C.ptr(po), ac, nn, pk, sd, ctl, mi,
+                            self.sm_count - self.sm_count // 3 if share else 0, st)
             elif isinstance(lyr, ConvLayer) and li in self.conv_tc:
                 t = self.conv_tc[li]
                 S_, O_, Ci, M_, f_ = lyr.in_sz, lyr.out_sz, lyr.num_prev_maps, lyr.num_maps, lyr.filter_sz
@@ -1024,6 +1036,10 @@ class NeuralNet():
             fn(*args)                                # warm-up (module loading, NCCL setup)
             self.launches[key[0]] = _C.lib.tn_launch_count() - n0   # kernels per replay
             torch.cuda.synchronize(self.device)
+            if self.dp_fused and self.dist.world > 1:
+                # the replay below recomputes the SAME parity of the peer-visible gradient buffers
+                # the warm-up just published: every rank must have finished reading them first
+                self.dist.barrier()
             for t, s in zip(restore, snap):
                 t.copy_(s)
             g = torch.cuda.CUDAGraph()
