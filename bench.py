@@ -549,8 +549,7 @@ def run_ours(args):
     parity = dp_parity(world, rank, dev, ctx) if world > 1 else None
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world, dev)
         return
     # whole-step view against the HBM roofline (SURVEY.md 8d figures)
     step_bytes = BYTES_PER_IMG * PER_GPU_BATCH + PARAM_BYTES_PER_STEP
@@ -576,17 +575,34 @@ def run_ours(args):
                          "L2; no explicit flush".format(nb, nb * PER_GPU_BATCH * IMG * IMG * 4 // 10 ** 6),
                    "cuda_graph": bool(net.use_graph),
                    "collective": ("none" if world == 1 else
+                                  "hybrid, inside the step's CUDA graph: NCCL all-reduce of the dense-layer "
+                                  "gradients overlapped with the conv backward pass + the late conv "
+                                  "gradients summed over CUDA-IPC peer memory (NVLink) in the update kernel"
+                                  if getattr(net, 'dp_hybrid', False) else
                                   "fused into the update kernel over CUDA-IPC peer memory (NVLink)"
-                                  if net.dp_fused else "NCCL all-reduce of the flat gradient buffer")},
+                                  if net.dp_fused else
+                                  "NCCL all-reduce of the flat gradient buffer"
+                                  + (" (in the CUDA graph, dense bucket overlapped)" if net.nccl_in_graph
+                                     else " (eager, between two CUDA graphs)"))},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roof, "cpu_baseline": cpu, "other_configs": others, "dp_parity": parity,
         "step_roofline": {"bound": "hbm", "algorithmic_bytes_per_step": step_bytes,
                           "achieved": step_gbs, "peak": hbm, "unit": "GB/s",
                           "frac": step_gbs / hbm, "flop_per_img": FLOP_PER_IMG},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    finish(world, dev)
+
+
+def finish(world, dev):
+    """Leave without tearing the NCCL communicator down: CUDA graphs that captured collectives are
+    still alive, and destroy_process_group() behind them has been seen to block."""
+    import torch
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -395,12 +395,16 @@ int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
  * words 0..7 receive the ranks' tokens, word 8 counts this rank's executions of the kernel),
  * mapped into this process with tn_ipc_open_handle (entry [rank] is the local buffer).  The kernel
  * signals and waits for all ranks, sums the buffers in rank order while it updates, and needs the
- * caller to alternate between two gradient buffers from step to step (see update.cu). */
+ * caller to alternate between two gradient buffers from step to step (see update.cu).
+ * peer_end (the offset of a segment, or 0 / total = everything): only flat indices below it are
+ * summed over the ranks here; the rest of the buffer and its NLL slot must already hold the sum
+ * over all ranks (NeuralNet all-reduces the big dense-layer gradients with NCCL while the conv
+ * layers are still back-propagating and leaves the few late conv gradients to this kernel). */
 int tn_allreduce_sgd_update(float *theta, float *vel, const float *const *peer_grads,
                             int *const *peer_flags, int world, int rank,
                             const tn_param_seg *segs_host, int nseg, int64_t total,
-                            const int32_t *ctl, float grad_scale, float nll_scale, float *cost_out,
-                            void *workspace, void *stream);
+                            int64_t peer_end, const int32_t *ctl, float grad_scale, float nll_scale,
+                            float *cost_out, void *workspace, void *stream);
 /* peer-mappable device memory (cudaMalloc, zero-filled) and CUDA-IPC handles (64 bytes) */
 int tn_peer_alloc(size_t bytes, void **ptr);
 int tn_peer_free(void *ptr);

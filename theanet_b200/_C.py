@@ -109,7 +109,7 @@ SIGNATURES = {
     'tn_update_workspace_bytes': (C.c_size_t, [_I, _I64]),
     'tn_sgd_momentum_maxnorm_update': (_I, [_P, _P, _P, C.POINTER(ParamSeg), _I, _I64, _P, _F,
                                             _P, _F, _P, _P, _P]),
-    'tn_allreduce_sgd_update': (_I, [_P, _P, _P, _P, _I, _I, C.POINTER(ParamSeg), _I, _I64, _P, _F, _F,
+    'tn_allreduce_sgd_update': (_I, [_P, _P, _P, _P, _I, _I, C.POINTER(ParamSeg), _I, _I64, _I64, _P, _F, _F,
                                      _P, _P, _P]),
     'tn_peer_alloc': (_I, [C.c_size_t, C.POINTER(C.c_void_p)]),
     'tn_peer_free': (_I, [_P]),

@@ -33,6 +33,8 @@ struct PeerArgs {
   int *flags[kMaxPeers];          // flags[r]: rank r's flag array (int[2*kMaxPeers]); [rank] is local:
                                   // words 0..7 tokens by source rank, word 8 the execution counter
   int world, rank;
+  int64_t peer_end;               // flat indices < peer_end are summed over the ranks here; the rest of
+                                  // the buffer (and the NLL slot) was all-reduced before this kernel
 };
 
 __device__ __forceinline__ void st_release_sys(int *p, int v) {
@@ -62,6 +64,11 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   __shared__ float red2[kUpdThreads];
   __shared__ int s_last;
   const int W = peers.world;
+  int s = 0;
+  while (s + 1 < tab.nseg && (int)blockIdx.x >= tab.first_block[s + 1]) ++s;
+  const tn_param_seg &sg = tab.seg[s];
+  const int64_t base = sg.offset + (int64_t)(blockIdx.x - tab.first_block[s]) * kUpdPerBlock;
+  const bool from_peers = W > 1 && base < peers.peer_end;     // segments never straddle peer_end
   int token = 0;
   if (W > 1) {
     token = __ldcg(peers.flags[peers.rank] + kMaxPeers) + 1;
@@ -69,19 +76,19 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
       __threadfence_system();
       st_release_sys(peers.flags[threadIdx.x] + peers.rank, token);   // "my gradients are complete"
     }
-    if (threadIdx.x < W) {
-      const int *f = peers.flags[peers.rank] + threadIdx.x;
-      const long long t0 = clock64();
-      while (ld_acquire_sys(f) - token < 0) {
-        if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died; fail loudly
+    // only the CTAs that read peer memory wait for the peers: with peer_end < total the bulk of
+    // the buffer was reduced earlier and its CTAs go straight to work, hiding the handshake
+    if (from_peers) {
+      if (threadIdx.x < W) {
+        const int *f = peers.flags[peers.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        while (ld_acquire_sys(f) - token < 0) {
+          if (clock64() - t0 > 20000000000ll) __trap();   // ~10 s: a peer died; fail loudly
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
-  int s = 0;
-  while (s + 1 < tab.nseg && (int)blockIdx.x >= tab.first_block[s + 1]) ++s;
-  const tn_param_seg &sg = tab.seg[s];
-  const int64_t base = sg.offset + (int64_t)(blockIdx.x - tab.first_block[s]) * kUpdPerBlock;
   const int64_t end = sg.offset + sg.size;
   const float lr = ctl_lr(ctl);
   const float step = __fmul_rn(sg.rate, lr);
@@ -92,7 +99,7 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   // data parallel: fetch this thread's 4 elements from every rank up front (4 x W independent
   // NVLink loads in flight, L1 bypassed: peer data changes every step), then add in rank order
   float gsum[4] = {0.f, 0.f, 0.f, 0.f};
-  if (W > 1) {
+  if (from_peers) {
     float gp[4][kMaxPeers];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -116,7 +123,7 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
       if (sg.l1 != 0.f) wsum = fmaf(sg.l1, fabsf(th), wsum);
       if (sg.l2 != 0.f) wsum = fmaf(sg.l2, th * th, wsum);
       if (sg.rate != 0.f) {
-        const float gi = W > 1 ? gsum[q] : grad[i];
+        const float gi = from_peers ? gsum[q] : grad[i];
         float g = grad_scale == 1.f ? gi : __fmul_rn(gi, grad_scale);
         if (sg.l1 != 0.f) {
           const float sgn = th > 0.f ? 1.f : (th < 0.f ? -1.f : 0.f);
@@ -168,8 +175,10 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   }
   if (threadIdx.x == 0) {
     float nll = 0.f;
-    if (W > 1) {
+    if (W > 1 && peers.peer_end >= nll_slot) {
       for (int r = 0; r < W; ++r) nll = __fadd_rn(nll, __ldcg(peers.grad[r] + nll_slot));
+    } else if (W > 1) {
+      nll = __ldcg(peers.grad[peers.rank] + nll_slot);        // already summed over the ranks
     } else if (nll_sum) {
       nll = nll_sum[0];
     }
@@ -313,14 +322,22 @@ extern "C" int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const fl
 extern "C" int tn_allreduce_sgd_update(float *theta, float *vel, const float *const *peer_grads,
                                        int *const *peer_flags, int world, int rank,
                                        const tn_param_seg *segs, int nseg, int64_t total,
-                                       const int32_t *ctl, float grad_scale, float nll_scale,
-                                       float *cost_out, void *workspace, void *stream) {
+                                       int64_t peer_end, const int32_t *ctl, float grad_scale,
+                                       float nll_scale, float *cost_out, void *workspace,
+                                       void *stream) {
   TN_REQUIRE(peer_grads && peer_flags && world >= 1 && world <= kMaxPeers && rank >= 0 &&
                  rank < world,
              TN_ERR_ARG, "tn_allreduce_sgd_update: bad peer arguments (world %d, rank %d)", world, rank);
   PeerArgs peers{};
   peers.world = world;
   peers.rank = rank;
+  peers.peer_end = (peer_end <= 0 || peer_end > total) ? total : peer_end;
+  if (peers.peer_end < total) {
+    bool on_boundary = false;
+    for (int s = 0; s < nseg; ++s) on_boundary |= segs[s].offset == peers.peer_end;
+    TN_REQUIRE(on_boundary, TN_ERR_ARG,
+               "tn_allreduce_sgd_update: peer_end %lld is not the start of a segment", (long long)peer_end);
+  }
   for (int r = 0; r < world; ++r) {
     TN_REQUIRE(peer_grads[r] && peer_flags[r], TN_ERR_ARG, "tn_allreduce_sgd_update: null peer %d", r);
     peers.grad[r] = peer_grads[r];

@@ -114,7 +114,12 @@ class NeuralNet():
         self.use_graph = use_graph and self.device.type == 'cuda'
         self.fuse_conv = fuse_conv
         self.fuse_head = fuse_head
-        self.nccl_in_graph = os.environ.get('TN_GRAPH_NCCL', '0') == '1'
+        # data parallel: the collective is captured into the step's CUDA graph and bucketed -- the
+        # gradients of the trailing dense layers (99% of the bytes in the shipped networks) are
+        # all-reduced on a side stream while the conv layers below are still back-propagating;
+        # TN_GRAPH_NCCL=0: graph -> one eager all-reduce -> graph (round 1)
+        self.nccl_in_graph = os.environ.get('TN_GRAPH_NCCL', '1') == '1'
+        self._comm = None
         self.overlap_wgrad = os.environ.get('TN_OVERLAP_WGRAD', '1') == '1'
         self.sm_count = (torch.cuda.get_device_properties(self.device).multi_processor_count
                          if self.device.type == 'cuda' else 148)
@@ -146,6 +151,7 @@ class NeuralNet():
         self.set_rate()
 
         self.step_count = 0
+        self._early_reduced = None
         self.inject = {}            # (layer index, 'noise'|'u'|'flip'|'mask') -> device tensor
         self.keep_conv_out = False  # also write the un-pooled output of fused conv+pool layers when training
         self.debug_elastic = False
@@ -217,7 +223,13 @@ class NeuralNet():
         # data parallel: either one NCCL all-reduce of `grad` per step, or (TN_DP_FUSED=1) the
         # all-reduce folded into the optimiser kernel over CUDA-IPC mapped peer buffers, with the
         # gradient buffer double-buffered by step parity (update.cu)
-        self.dp_fused = self.dist.world > 1 and os.environ.get('TN_DP_FUSED', '0') == '1'
+        # default (hybrid): the big early bucket goes through NCCL inside the graph, overlapped with
+        # the conv backward pass; the few late conv gradients are summed over peer memory by the
+        # update kernel itself (no second collective, no launch gap before the update)
+        self.dp_hybrid = (self.dist.world > 1 and self.nccl_in_graph and
+                          os.environ.get('TN_DP_HYBRID', '1') == '1' and self.device.type == 'cuda')
+        self.dp_fused = self.dist.world > 1 and (os.environ.get('TN_DP_FUSED', '0') == '1' or
+                                                 self.dp_hybrid)
         if self.dp_fused:
             from .dist import PeerBuffers
             self.peers = PeerBuffers(self.dist, total + 4, dev)
@@ -726,10 +738,46 @@ class NeuralNet():
             yield ctypes.c_void_p(side.cuda_stream)
 
     def _join_wgrad(self):
+        main = torch.cuda.current_stream(self.device)
         if self.overlap_wgrad and self._side is not None:
-            main = torch.cuda.current_stream(self.device)
             for side in self._side:
                 main.wait_stream(side)
+        if self._early_reduced:
+            main.wait_stream(self._comm)
+
+    def _bucket_split(self):
+        """(index of the lowest layer of the trailing run of dense layers, its offset in the flat
+        gradient buffer) when the data-parallel all-reduce can be split there, else None: the early
+        bucket [offset, end + NLL slot) is complete once that layer's weight gradient is, long
+        before the conv layers below have finished."""
+        if not (self.dist.world > 1 and self.nccl_in_graph and self.head and
+                (self.dp_hybrid or not self.dp_fused)):
+            return None
+        L = self.tr_layers
+        li = len(L) - 1
+        while li > 0 and (isinstance(L[li], DropOutLayer) or
+                          (isinstance(L[li], HiddenLayer) and not isinstance(L[li], SoftAuxLayer))):
+            li -= 1
+        first = li + 1
+        while first < len(L) and not L[first].params:
+            first += 1
+        if first >= len(L) or not any(self.trainable[j] for j in range(1, first)):
+            return None
+        return first, self.param_offset[id(L[first].params[0])]
+
+    def _reduce_early_bucket(self, offset):
+        """All-reduce grad[offset:] (dense-layer gradients + the NLL slot) on the communication
+        stream, behind every weight-gradient kernel enqueued so far."""
+        main = torch.cuda.current_stream(self.device)
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(self.device)
+        self._comm.wait_stream(main)
+        if self.overlap_wgrad and self._side is not None:
+            for side in self._side:
+                self._comm.wait_stream(side)
+        with torch.cuda.stream(self._comm):
+            self.dist.all_reduce_sum(self.grad[offset:])
+        self._early_reduced = offset
 
     def _backward(self):
         st = self._stream()
@@ -738,7 +786,11 @@ class NeuralNet():
         L = self.tr_layers
         g = self.gsoft                       # dL/dz of the layer being visited
         g_bf16 = None                        # ... or, inside the bf16 conv stack, an NHWC bf16 tensor
+        bucket = self._bucket_split()
+        self._early_reduced = None
         for li in range(len(L) - 1, 0, -1):
+            if bucket and li == bucket[0] - 1:       # every dense layer above has been enqueued
+                self._reduce_early_bucket(bucket[1])
             lyr = L[li]
             x = self.out[li - 1]
             below = self.need_below[li]
@@ -963,12 +1015,16 @@ class NeuralNet():
         if self.dp_fused:                            # all-reduce inside the optimiser kernel
             _C.call('tn_allreduce_sgd_update', _C.ptr(self.theta), _C.ptr(self.vel),
                     self.peers.grad_ptrs[self._grad_parity], self.peers.flag_ptrs, self.dist.world,
-                    self.dist.rank, self.segs, self.n_segs, self.n_flat, _C.ptr(self.ctl), 1.0,
+                    self.dist.rank, self.segs, self.n_segs, self.n_flat,
+                    int(self._early_reduced or 0), _C.ptr(self.ctl), 1.0,
                     1.0 / self.batch_sz, _C.ptr(self.cost), _C.ptr(self.ws_update), st)
             return
         if self.dist.world > 1 and not self.nccl_in_graph:
             return                                   # the caller reduces, then _update_launches
-        self.dist.all_reduce_sum(self.grad)          # the one collective of the step
+        if self._early_reduced:                      # the small rest: conv gradients
+            self.dist.all_reduce_sum(self.grad[:self._early_reduced])
+        else:
+            self.dist.all_reduce_sum(self.grad)      # the one collective of the step
         self._update_launches()
 
     def _update_launches(self):
@@ -1043,7 +1099,9 @@ class NeuralNet():
             for t, s in zip(restore, snap):
                 t.copy_(s)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread_local: other threads (the NCCL watchdog polling its events) may keep issuing
+            # CUDA calls while this thread captures; the default 'global' mode fails the capture
+            with torch.cuda.graph(g, capture_error_mode='thread_local'):
                 fn(*args)
             self._graphs[key] = g
         g.replay()

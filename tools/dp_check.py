@@ -69,8 +69,13 @@ def main():
         assert worst < 1e-3
         print('DP_CHECK_OK world=%d graph=%d worst=%.2e' % (ctx.world, a.graph, worst), flush=True)
     if ctx.world > 1:
+        # leave without tearing the communicator down: the CUDA graphs that captured collectives
+        # are still alive, and destroy_process_group() behind them has been seen to block
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize(dev)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':

@@ -26,11 +26,20 @@ def main():
     a = ap.parse_args()
     import torch
     from torch.profiler import profile, ProfilerActivity
-    from theanet_b200.neuralnet import NeuralNet
+    from theanet_b200.neuralnet import NeuralNet, DistContext
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    ctx = DistContext()
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+    torch.cuda.set_device(dev)
+    if world > 1:                                   # under torchrun: the data-parallel step
+        dist.init_process_group('nccl', device_id=dev)
+        ctx = DistContext(rank, world, None)
     c = bench.CONFIGS[a.cfg]
-    prms = bench.load_prms(c['per_gpu'], a.cfg)
-    x, y = bench.synth_corpus(8 * c['per_gpu'], a.cfg)
-    net = NeuralNet(prms['layers'], prms['training_params'])
+    prms = bench.load_prms(c['per_gpu'] * world, a.cfg)
+    x, y = bench.synth_corpus(8 * c['per_gpu'] * world, a.cfg)
+    net = NeuralNet(prms['layers'], prms['training_params'], device=dev, dist=ctx)
     fn = net.get_trin_model(x, y, lazy=True)
     for s in range(20):
         fn(s % 8)
@@ -39,6 +48,9 @@ def main():
         for s in range(a.steps):
             fn(s % 8)
         torch.cuda.synchronize()
+    if rank != 0:
+        dist.barrier()
+        os._exit(0)
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA
            and 'memcpy' not in e.name.lower() and 'memset' not in e.name.lower()]
     evs.sort(key=lambda e: e.time_range.start)
@@ -71,7 +83,11 @@ def main():
         busy, max(r['end_us'] for r in rows)))
     if a.out:
         with open(a.out, 'w') as f:
-            json.dump({'cfg': a.cfg, 'period_us': period, 'kernels': rows}, f, indent=1)
+            json.dump({'cfg': a.cfg, 'world': world, 'period_us': period, 'kernels': rows}, f, indent=1)
+    if world > 1:
+        dist.barrier()
+        sys.stdout.flush()
+        os._exit(0)
 
 
 if __name__ == '__main__':
