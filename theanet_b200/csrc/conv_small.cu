@@ -45,6 +45,8 @@ struct SmallArgs {
   uint8_t *tie;         // per pooled cell: bit (2*dy+dx) set where a[2pi+dy, 2pj+dx] == pooled
   float *partial, *teampart;
   unsigned *tickets;
+  unsigned *gbar;       // grid barrier {arrivals, generation} of the cooperative final reduction
+  int coop;             // 1: every CTA of the grid is resident at once (host checked the occupancy)
   long long *dbg;       // optional phase timestamps (tools/phase_times.py), 64 per CTA
   int B, C, S, M, O, P, Pc, NB;
   int Sp;               // forward: even row pitch of the staged images (8-byte patch loads)
@@ -295,6 +297,62 @@ __device__ __noinline__ void small_finish(const SmallArgs &k, float *red, float 
   for (int t = nW + mP + tid; t < k.nout4; t += kST) pout[t] = 0.f;
 
   TN_PHASE(56);
+  if (k.coop) {
+    // ---- all CTAs are resident: one grid barrier, then EVERY CTA sums a few outputs over all the
+    // partials (thread t takes partials t, t+256, ... in order, then a fixed-shape tree:
+    // deterministic) -- instead of two ticket levels that end in one CTA summing everything.
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      unsigned gen;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(k.gbar + 1) : "memory");
+      if (atomicAdd(k.gbar, 1u) == gridDim.x - 1) {
+        k.gbar[0] = 0u;                                   // ready for the next launch
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(k.gbar + 1), "r"(gen + 1u) : "memory");
+      } else {
+        unsigned now;
+        const long long t0 = clock64();
+        do {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(k.gbar + 1) : "memory");
+          if (clock64() - t0 > 4000000000ll) __trap();    // not co-resident after all: fail loudly
+        } while (now == gen);
+      }
+    }
+    __syncthreads();
+    TN_PHASE(57);
+    const int nout = nW + M;
+    const int per = (nout + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int o0 = blockIdx.x * per, o1 = min(o0 + per, nout);
+    float *wred = dbs;                                    // 8 warps x outputs, reused
+    for (int o = o0; o < o1; ++o) {
+      const int src = o < nW ? o : nW + (o - nW);         // [nW, nW + M): bias gradient
+      float sv = 0.f;
+      for (int pc = tid; pc < (int)gridDim.x; pc += kST) sv += __ldcg(k.partial + (size_t)pc * k.nout4 + src);
+#pragma unroll
+      for (int sh = 16; sh > 0; sh >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, sh);
+      if ((tid & 31) == 0) wred[tid >> 5] = sv;
+      __syncthreads();
+      if (tid == 0) {
+        float tot = wred[0];
+#pragma unroll
+        for (int w = 1; w < kST / 32; ++w) tot += wred[w];
+        if (o < nW) {   // o = ((mg*C + c)*4 + q)*FF + u*F + v   (correlation taps: flip back)
+          const int e = o % FF;
+          int r = o / FF;
+          const int q = r & 3; r >>= 2;
+          const int cc = r % C, g = r / C;
+          const int m = 4 * g + q, u = e / F, v = e - u * F;
+          if (m < M) k.dW[((m * C + cc) * F + (F - 1 - u)) * F + (F - 1 - v)] = tot;
+        } else {
+          k.db[o - nW] = tot;
+        }
+      }
+      __syncthreads();
+    }
+    TN_PHASE(58);
+    return;
+  }
   // ---- two-level ticket: last CTA of a team sums the team, last team sums the teams --------
   const int team = blockIdx.x / k.team;
   const int nteam = (gridDim.x + k.team - 1) / k.team;
@@ -961,6 +1019,21 @@ static int small_smem_attr(K kernel, size_t smem, const char *who) {
   return TN_OK;
 }
 
+// 1 when `grid` CTAs of `kernel` (kST threads, `smem` dynamic bytes) fit on the device at once,
+// i.e. a grid-wide barrier inside the kernel cannot deadlock (TN_SMALL_COOP=0: never)
+template <typename K>
+static int small_coresident(K kernel, int grid, size_t smem) {
+  if (env_int("TN_SMALL_COOP", 1) == 0) return 0;
+  int per_sm = 0, dev = 0, sms = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kST, smem) != cudaSuccess ||
+      cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return (long long)per_sm * sms >= grid ? 1 : 0;
+}
+
 int small_fprop(const float *x, const float *W, const float *bias, float *a, float *pooled,
                 uint8_t *tie, int B, int C, int S, int M, int O, int act, int act_nn, int P,
                 cudaStream_t st) {
@@ -983,7 +1056,7 @@ static size_t small_bwd_workspace_bytes_for(const SmallPlan &pl, int C, int M) {
   const int nout4 = (G * C * 4 * kSF * kSF + 4 * G + 3) / 4 * 4;
   const int nteam = ceil_div(pl.grid, pl.team);
   return ((size_t)pl.grid * nout4 + (size_t)nteam * nout4) * sizeof(float) +
-         (size_t)(nteam + 1 + 3) / 4 * 4 * sizeof(unsigned);
+         (size_t)(nteam + 1 + 2 + 3) / 4 * 4 * sizeof(unsigned);   // tickets + grid barrier
 }
 
 // weight gradient without dx (small_wgrad_kernel): only the images are staged
@@ -1051,15 +1124,18 @@ int small_bwd(const float *x, const float *a, const uint8_t *tie, const float *p
   k.partial = (float *)workspace;
   k.teampart = k.partial + (size_t)pl.grid * k.nout4;
   k.tickets = reinterpret_cast<unsigned *>(k.teampart + (size_t)nteam * k.nout4);
+  k.gbar = k.tickets + nteam + 1;
   if (direct) {
     int rc = small_smem_attr(small_wgrad_kernel<kSF>, pl.smem, who);
     if (rc) return rc;
+    k.coop = small_coresident(small_wgrad_kernel<kSF>, pl.grid, pl.smem);
     launch_pdl(small_wgrad_kernel<kSF>, dim3(pl.grid), dim3(kST), pl.smem, st, k);
     TN_LAUNCH_CHECK(who);
     return TN_OK;
   }
   int rc = small_smem_attr(small_bwd_kernel<kSF>, pl.smem, who);
   if (rc) return rc;
+  k.coop = small_coresident(small_bwd_kernel<kSF>, pl.grid, pl.smem);
   launch_pdl(small_bwd_kernel<kSF>, dim3(pl.grid), dim3(kST), pl.smem, st, k);
   TN_LAUNCH_CHECK(who);
   return TN_OK;
