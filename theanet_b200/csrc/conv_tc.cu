@@ -403,25 +403,47 @@ __global__ void conv_tc_wgrad_finish_kernel(const float *__restrict__ partial, i
 
 // db[m] = sum_p gz[p][m] (bf16 NHWC, fp32 accumulate), two fixed-order stages:
 // stage 1: CTA (channel block of 64, pixel slice) -> partial[slice][m]; stage 2 adds the slices.
-constexpr int kColSlices = 128;
+constexpr int kColSlices = 296;     // two CTAs per SM
+// a thread owns 8 consecutive channels (one 16-byte load per pixel), M/8 threads span a pixel row
+// and the CTA walks 1024/(M/8) pixels per pass with four loads in flight per thread: HBM-bound
+// (the first version read 2 bytes per thread per dependent iteration and ran at a third of that)
 __global__ void __launch_bounds__(1024)
 colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ gz, int64_t P, int M,
                    float *__restrict__ partial) {
-  __shared__ float red[16][65];
-  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
-  const int m = blockIdx.x * 64 + tx;
-  const int64_t per = (P + gridDim.y - 1) / gridDim.y;
-  const int64_t p0 = blockIdx.y * per, p1 = p0 + per < P ? p0 + per : P;
-  float s = 0.f;
-  if (m < M)
-    for (int64_t p = p0 + ty; p < p1; p += 16) s += __bfloat162float(gz[p * M + m]);
-  red[ty][tx] = s;
-  __syncthreads();
-  if (ty == 0 && m < M) {
-    float t = red[0][tx];
+  __shared__ float red[1024 * 8];
+  const int vpr = M >> 3;                         // threads per pixel
+  const int rpp = 1024 / vpr;                     // pixels per pass
+  const int tx = threadIdx.x % vpr, ty = threadIdx.x / vpr;
+  const int64_t per = (P + gridDim.x - 1) / gridDim.x;
+  const int64_t p0 = blockIdx.x * per, p1 = p0 + per < P ? p0 + per : P;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (ty < rpp) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(gz) + tx;
+    for (int64_t p = p0 + ty; p < p1; p += 4 * rpp) {
+      uint4 v[4];
 #pragma unroll
-    for (int k = 1; k < 16; ++k) t += red[k][tx];
-    partial[(size_t)blockIdx.y * M + m] = t;
+      for (int u = 0; u < 4; ++u) {
+        const int64_t q = p + (int64_t)u * rpp;
+        v[u] = q < p1 ? __ldg(src + q * vpr) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {             // bf16 -> fp32 is a 16-bit shift
+          acc[2 * j] += __uint_as_float(w[j] << 16);
+          acc[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[ty * M + 8 * tx + j] = acc[j];
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < M; m += 1024) {
+    float t = 0.f;
+    for (int k = 0; k < rpp; ++k) t += red[k * M + m];
+    partial[(size_t)blockIdx.x * M + m] = t;
   }
 }
 __global__ void colsum_finish_kernel(const float *__restrict__ partial, int nslices, int M,
@@ -905,8 +927,8 @@ extern "C" int tn_conv2d_tc_wgrad(const void *x, const void *gz, float *dW, floa
       (const float *)workspace, g.nsplit, M, C, f, dW);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(finish)");
   float *cpart = (float *)workspace + (size_t)g.nsplit * f * f * M * C;
-  colsum_bf16_kernel<<<dim3(ceil_div(M, 64), kColSlices), 1024, 0, st>>>(
-      (const __nv_bfloat16 *)gz, (int64_t)B * out_sz * out_sz, M, cpart);
+  colsum_bf16_kernel<<<kColSlices, 1024, 0, st>>>((const __nv_bfloat16 *)gz,
+                                                   (int64_t)B * out_sz * out_sz, M, cpart);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(db partial)");
   colsum_finish_kernel<<<ceil_div(M, 128), 128, 0, st>>>(cpart, kColSlices, M, db);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(db)");

@@ -282,7 +282,10 @@ class NeuralNet():
         last = self.tr_layers[-1]
         n_out = last.n_out
         self.z = self.out[-1]                                   # pre-softmax scores
-        self.logprob = torch.empty((B, n_out), dtype=f32, device=dev)
+        # log-probabilities and the cost share one buffer: a call that returns them to the host
+        # (the reference's training function does, neuralnet.py:236-241) needs ONE device-to-host copy
+        self._res = torch.zeros(B * n_out + 4, dtype=f32, device=dev)
+        self.logprob = self._res[:B * n_out].view(B, n_out)
         # output stage (outlayers.py): kind of layer, loss; SoftmaxLayer + 'nll' is the hot path
         self.out_kind = OUT_KINDS[last.kind]
         self.loss_code, self.log_thr = last.cost()
@@ -292,7 +295,7 @@ class NeuralNet():
             if self.out_kind == _C.OUT_EXPLOSS else self.logprob
         self.gsoft = torch.empty((B, n_out), dtype=f32, device=dev)
         self.rowloss = torch.empty(B, dtype=f32, device=dev)
-        self.cost = torch.zeros(1, dtype=f32, device=dev)
+        self.cost = self._res[B * n_out:B * n_out + 1]
         self.stats = torch.zeros(2 + 2 * B, dtype=f32, device=dev)
         self.preds = torch.zeros(B, dtype=torch.int64, device=dev)
         for l in (last, self.te_layers[-1]):
@@ -1163,21 +1166,24 @@ class NeuralNet():
         auxd = self._stage_aux(aux_data, resident)
         B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
         key = ('train', id(xd), take_index_list)
-        h_cost = torch.zeros(1, dtype=torch.float32, pin_memory=self.device.type == 'cuda')
-        h_lp = torch.zeros(self.logprob.shape, dtype=torch.float32,
-                           pin_memory=self.device.type == 'cuda')
+        pin = self.device.type == 'cuda'
+        n_lp = self.logprob.numel()
+        h_res = torch.zeros(self._res.shape, dtype=torch.float32, pin_memory=pin)
+        h_res_np = h_res.numpy()
+        lp_shape = tuple(self.logprob.shape)
         two = self.feat is not self.logprob          # ExpLossLayer: features != logprob
-        h_ft = torch.zeros_like(h_lp, pin_memory=self.device.type == 'cuda') if two else None
+        h_ft = torch.zeros(lp_shape, dtype=torch.float32, pin_memory=pin) if two else None
 
         def results():
-            """[cost, features, logprob] on the host (neuralnet.py:236-241)."""
-            h_cost.copy_(self.cost, non_blocking=True)
-            h_lp.copy_(self.logprob, non_blocking=True)
+            """[cost, features, logprob] on the host (neuralnet.py:236-241): one device-to-host
+            copy of [logprob | cost], one synchronisation."""
+            h_res.copy_(self._res, non_blocking=True)
             if two:
                 h_ft.copy_(self.feat, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            lp = h_lp.numpy().copy()
-            return [h_cost.numpy()[0].copy(), h_ft.numpy().copy() if two else lp, lp]
+            if pin:
+                torch.cuda.current_stream(self.device).synchronize()
+            lp = h_res_np[:n_lp].reshape(lp_shape).copy()
+            return [h_res_np[n_lp].copy(), h_ft.numpy().copy() if two else lp, lp]
 
         # host-resident corpus: double-buffered minibatch staging.  While step i runs, the H2D copy
         # of batch i+1 (the reference driver walks the batches in order, train.py:210) proceeds on a
