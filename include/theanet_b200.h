@@ -391,7 +391,7 @@ int tn_sgd_momentum_maxnorm_update(float *theta, float *vel, const float *grad,
                                    void *stream);
 /* Data parallel, fused: the same update with the gradient all-reduce folded in.  peer_grads[r] /
  * peer_flags[r] (host arrays of `world` device pointers) are rank r's flat gradient buffer
- * (total + 4 floats; [total] is its NLL partial sum) and flag array (int[16], zero-filled once:
+ * (total + 4 floats; [total] is its NLL partial sum) and flag array (int[32], zero-filled once:
  * words 0..7 receive the ranks' tokens, word 8 counts this rank's executions of the kernel),
  * mapped into this process with tn_ipc_open_handle (entry [rank] is the local buffer).  The kernel
  * signals and waits for all ranks, sums the buffers in rank order while it updates, and needs the
@@ -405,6 +405,13 @@ int tn_allreduce_sgd_update(float *theta, float *vel, const float *const *peer_g
                             const tn_param_seg *segs_host, int nseg, int64_t total,
                             int64_t peer_end, const int32_t *ctl, float grad_scale, float nll_scale,
                             float *cost_out, void *workspace, void *stream);
+/* Two-shot all-reduce (sum) of peer_bufs[*][offset, offset + count) over peer memory, in place: every
+ * rank reduces 1/world of the range from all ranks (rank order: bit-identical totals everywhere),
+ * then gathers the other ranks' totals.  peer_bufs / peer_flags as above, except that the flag arrays
+ * must hold int[32] (words 16..25 belong to this kernel).  Like tn_allreduce_sgd_update it relies on
+ * the caller alternating between two buffers from step to step.  offset, count: multiples of 4. */
+int tn_peer_allreduce(float *const *peer_bufs, int *const *peer_flags, int world, int rank,
+                      int64_t offset, int64_t count, void *stream);
 /* peer-mappable device memory (cudaMalloc, zero-filled) and CUDA-IPC handles (64 bytes) */
 int tn_peer_alloc(size_t bytes, void **ptr);
 int tn_peer_free(void *ptr);

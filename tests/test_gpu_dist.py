@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 MODES = {'nccl': dict(TN_DP_HYBRID='0', TN_DP_FUSED='0'),       # one all-reduce, early bucket overlapped
          'nccl_eager': dict(TN_DP_HYBRID='0', TN_DP_FUSED='0', TN_GRAPH_NCCL='0'),   # graph, eager all-reduce, graph
-         'hybrid': dict(TN_DP_HYBRID='1', TN_DP_FUSED='0'),     # default: NCCL early bucket + peer-memory tail
+         'hybrid': dict(TN_DP_HYBRID='1', TN_DP_FUSED='0'),     # default: two-shot peer-memory all-reduce of the early bucket + peer-memory tail
+         'hybrid_nccl': dict(TN_DP_HYBRID='1', TN_DP_FUSED='0', TN_PEER_AR='0'),   # NCCL early bucket + peer-memory tail
          'fused': dict(TN_DP_HYBRID='0', TN_DP_FUSED='1')}      # everything over peer memory in the update kernel
 
 

@@ -111,6 +111,7 @@ SIGNATURES = {
                                             _P, _F, _P, _P, _P]),
     'tn_allreduce_sgd_update': (_I, [_P, _P, _P, _P, _I, _I, C.POINTER(ParamSeg), _I, _I64, _I64, _P, _F, _F,
                                      _P, _P, _P]),
+    'tn_peer_allreduce': (_I, [_P, _P, _I, _I, _I64, _I64, _P]),
     'tn_peer_alloc': (_I, [C.c_size_t, C.POINTER(C.c_void_p)]),
     'tn_peer_free': (_I, [_P]),
     'tn_ipc_get_handle': (_I, [_P, _P]),

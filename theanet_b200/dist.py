@@ -82,9 +82,9 @@ class PeerBuffers:
             _C.call('tn_ipc_get_handle', ptr, buf)
             return buf.raw
 
-        own = [alloc(4 * nfloats), alloc(4 * nfloats), alloc(4 * 16)]   # flags: 8 tokens + the epoch word
+        own = [alloc(4 * nfloats), alloc(4 * nfloats), alloc(4 * 32)]   # flags: update kernel words 0..8, all-reduce kernel words 16..25
         self.grad = [torch.as_tensor(_RawCuda(own[k], nfloats, '<f4'), device=device) for k in (0, 1)]
-        self.flags = torch.as_tensor(_RawCuda(own[2], 16, '<i4'), device=device)
+        self.flags = torch.as_tensor(_RawCuda(own[2], 32, '<i4'), device=device)
         torch.cuda.synchronize(device)
         mine = [handle(p) for p in own]
         everyone = [None] * W

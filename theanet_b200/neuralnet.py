@@ -230,6 +230,7 @@ class NeuralNet():
                           os.environ.get('TN_DP_HYBRID', '1') == '1' and self.device.type == 'cuda')
         self.dp_fused = self.dist.world > 1 and (os.environ.get('TN_DP_FUSED', '0') == '1' or
                                                  self.dp_hybrid)
+        self.peer_ar = os.environ.get('TN_PEER_AR', '1') == '1'    # 0: NCCL for the big bucket
         if self.dp_fused:
             from .dist import PeerBuffers
             self.peers = PeerBuffers(self.dist, total + 4, dev)
@@ -779,7 +780,16 @@ class NeuralNet():
             for side in self._side:
                 self._comm.wait_stream(side)
         with torch.cuda.stream(self._comm):
-            self.dist.all_reduce_sum(self.grad[offset:])
+            if self.dp_hybrid and self.peer_ar:
+                # two-shot reduce-scatter + all-gather over peer memory (tn_peer_allreduce): at 8
+                # ranks the NCCL ring takes 56 us for this 1.4 MB bucket and outlasts the conv
+                # backward pass it is supposed to hide behind
+                n = self.n_flat + 4 - offset
+                _C.call('tn_peer_allreduce', self.peers.grad_ptrs[self._grad_parity],
+                        self.peers.flag_ptrs, self.dist.world, self.dist.rank, offset, n,
+                        ctypes.c_void_p(self._comm.cuda_stream))
+            else:
+                self.dist.all_reduce_sum(self.grad[offset:])
         self._early_reduced = offset
 
     def _backward(self):
