@@ -545,3 +545,35 @@ def test_3flat_prms_at_the_bench_batch_size():
     prms = load_prms('3flat.prms', 1024, 28)
     x, y = synth(2048, 1, 28, 457)
     run_pair(prms, x, y, 3, True, check_at=(1, 3))
+
+
+def test_batch_index_bounds_and_graph_lifetime():
+    """a batch index past the corpus must raise (the reference's Theano slice would) instead
+    of reading out of bounds, and the captured graphs of a closure die with it (they bake the raw
+    pointers of ITS staged corpus; a recycled id() must never find them)."""
+    import gc
+    from theanet_b200.neuralnet import NeuralNet
+    prms = load_prms('mnist.prms', 16, 28)
+    x, y = synth(48, 1, 28, 10)
+    net = NeuralNet(prms['layers'], prms['training_params'])
+    fn = net.get_trin_model(x, y)
+    te = net.get_test_model(x, y)
+    fn(0), fn(2), te(2)
+    with pytest.raises(IndexError):
+        fn(3)
+    with pytest.raises(IndexError):
+        te(3)
+    with pytest.raises(IndexError):
+        fn(-1)
+    fn_idx = net.get_trin_model(x, y, take_index_list=True)
+    fn_idx(np.arange(16))
+    with pytest.raises(IndexError):
+        fn_idx(np.arange(40, 56))
+    n_graphs = len(net._graphs)
+    assert n_graphs >= 3
+    del fn, te, fn_idx
+    gc.collect()
+    assert len(net._graphs) == 0
+    fn2 = net.get_trin_model(x[:32], y[:32])
+    cost, _, _ = fn2(1)
+    assert np.isfinite(cost)

@@ -20,6 +20,7 @@ PyTorch is used for device memory, streams, CUDA graphs and torch.distributed on
 """
 import ctypes
 import os
+import weakref
 from contextlib import contextmanager
 from types import SimpleNamespace
 from functools import reduce
@@ -1175,7 +1176,10 @@ class NeuralNet():
         xd, yd, host = self._stage(x_data, y_data, resident)
         auxd = self._stage_aux(aux_data, resident)
         B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
-        key = ('train', id(xd), take_index_list)
+        # captured graphs bake the raw device pointers of THIS closure's staged corpus: key them by a
+        # serial number (id(xd) can be recycled once a closure is collected) and drop them with it
+        key = ('train', self._new_model_key(), take_index_list)
+        n_rows = int(host[0].shape[0] if host is not None else xd.shape[0])
         pin = self.device.type == 'cuda'
         n_lp = self.logprob.numel()
         h_res = torch.zeros(self._res.shape, dtype=torch.float32, pin_memory=pin)
@@ -1218,8 +1222,16 @@ class NeuralNet():
         else:
             bufs = None
 
+        def check_batch(i):
+            # the reference slices a shared variable and Theano raises on a short batch
+            if not (0 <= int(i) and (int(i) + 1) * B <= n_rows):
+                raise IndexError("minibatch {} of {} images is outside the corpus of {} rows".format(
+                    int(i), B, n_rows))
+
         def training_fn(indx):
             self._aux_corpus = auxd
+            if not take_index_list:
+                check_batch(indx)
             if bufs is not None:
                 if pre['index'] == int(indx):
                     slot = pre['slot']
@@ -1241,6 +1253,8 @@ class NeuralNet():
                 return results()
             if take_index_list:
                 ids = np.asarray(indx, dtype=np.int32)[rank * Bl:(rank + 1) * Bl]
+                if ids.size != Bl or ids.min() < 0 or ids.max() >= n_rows:
+                    raise IndexError("index list must hold BATCH_SZ row numbers in [0, {})".format(n_rows))
                 if host is None:
                     self._upload_idx(ids)
                     idx, row0 = self.idx, 0
@@ -1264,7 +1278,16 @@ class NeuralNet():
                 return self.cost, self.feat, self.logprob
             return results()
 
+        weakref.finalize(training_fn, self._drop_graphs, key[1])
         return training_fn
+
+    def _new_model_key(self):
+        self._model_serial = getattr(self, '_model_serial', 0) + 1
+        return self._model_serial
+
+    def _drop_graphs(self, serial):
+        for k in [k for k in self._graphs if len(k) > 1 and k[1] == serial]:
+            del self._graphs[k]
 
     def reset_accumulated_gradients(self):
         self.vel.zero_()
@@ -1274,10 +1297,14 @@ class NeuralNet():
         xd, yd, host = self._stage(x_data, y_data, resident)
         auxd = self._stage_aux(aux_data, resident)
         B, Bl, rank = self.batch_sz, self.local_bsz, self.dist.rank
-        key = ('test', id(xd))
+        key = ('test', self._new_model_key())
+        n_rows = int(host[0].shape[0] if host is not None else xd.shape[0])
 
         def test_fn(indx):
             self._aux_corpus = auxd
+            if not (0 <= int(indx) and (int(indx) + 1) * B <= n_rows):
+                raise IndexError("minibatch {} of {} images is outside the corpus of {} rows".format(
+                    int(indx), B, n_rows))
             lo = int(indx) * B + rank * Bl
             if host is None:
                 row0 = lo
@@ -1293,6 +1320,7 @@ class NeuralNet():
                 outs += [self.feat.cpu().numpy(), self.preds.cpu().numpy()]
             return outs
 
+        weakref.finalize(test_fn, self._drop_graphs, key[1])
         return test_fn
 
     def takes_aux(self):
