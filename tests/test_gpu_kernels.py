@@ -920,3 +920,34 @@ def test_subsample_and_its_gradient(C, planes, S, s):
     want = np.zeros((planes, S, S), np.float32)
     want[:, :O * s:s, :O * s:s] = g
     assert np.array_equal(up.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize('world', [1, 2, 4])
+def test_peer_allreduce_two_shot_on_one_device(C, world):
+    """tn_peer_allreduce with all `world` ranks living on ONE device (a rank = a buffer + a flag array +
+    a stream): the kernels of the ranks run concurrently and go through the real two-phase
+    handshake (reduce-scatter, all-gather).  Every rank must end with the same bits: the sum in rank
+    order.  Repeated launches exercise the execution-counter tokens and the ticket reset."""
+    import ctypes
+    rng = np.random.default_rng(77 + world)
+    off, n = 8, 4 * 3001                      # a range inside a larger buffer, ragged slices
+    total = off + n + 12
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    flags = [torch.zeros(32, dtype=torch.int32, device='cuda') for _ in range(world)]
+    arr = ctypes.c_void_p * world
+    for rep in range(3):
+        host = [rng.standard_normal(total).astype(np.float32) for _ in range(world)]
+        bufs = [dev(h) for h in host]
+        want = host[0][off:off + n].copy()
+        for r in range(1, world):
+            want = want + host[r][off:off + n]             # float32 adds in rank order
+        bp, fp = arr(*[b.data_ptr() for b in bufs]), arr(*[f.data_ptr() for f in flags])
+        sync()
+        for r in range(world):
+            C.call('tn_peer_allreduce', bp, fp, world, r, off, n, ctypes.c_void_p(streams[r].cuda_stream))
+        sync()
+        for r in range(world):
+            got = bufs[r].cpu().numpy()
+            assert np.array_equal(got[off:off + n], want), (rep, r)
+            assert np.array_equal(got[:off], host[r][:off]) and np.array_equal(got[off + n:], host[r][off + n:])
+        assert all(int(f[24]) == rep + 1 and int(f[25]) == 0 for f in flags)

@@ -311,6 +311,8 @@ class NeuralNet():
         pin = self.device.type == 'cuda'
         self.ctl = torch.zeros(_C.CTL_WORDS, dtype=torch.int32, device=dev)
         self._ctl_np = np.zeros(_C.CTL_WORDS, dtype=np.int32)      # host mirror of the last write
+        self._ctl_ptr = self.ctl.data_ptr()
+        self._lr_cached = (None, 0)
         self._idx_ring = [torch.zeros(B, dtype=torch.int32, pin_memory=pin) for _ in range(8)]
         self._idx_ev = [None] * len(self._idx_ring)
         self._idx_k = 0
@@ -967,14 +969,18 @@ class NeuralNet():
             g = dx
 
     def _set_ctl(self, row0):
-        c = self._ctl_np
-        c[_C.CTL_STEP] = self.step_count & 0x7fffffff
-        c[_C.CTL_SAMPLE0] = self.dist.rank * self.local_bsz
-        c[_C.CTL_ROW0] = int(row0)
-        c[_C.CTL_LR_BITS] = int(np.float32(self.cur_learn_rate.get_value()).view(np.int32))
-        if self.device.type == 'cuda':        # eager, stream-ordered ahead of the step's graph
-            _C.call('tn_set_ctl', _C.ptr(self.ctl), int(c[_C.CTL_STEP]), int(c[_C.CTL_SAMPLE0]),
-                    int(c[_C.CTL_ROW0]), int(c[_C.CTL_LR_BITS]), self._stream())
+        """Per-step scalars -> the device control block, as the launch arguments of tn_set_ctl
+        (eager, stream-ordered ahead of the step's graph).  Kept lean: it sits on the host's critical
+        path between two steps of the synchronous API."""
+        lr = self.cur_learn_rate.get_value()
+        if lr != self._lr_cached[0]:
+            self._lr_cached = (lr, int(np.float32(lr).view(np.int32)))
+        step, s0 = self.step_count & 0x7fffffff, self.dist.rank * self.local_bsz
+        c = self._ctl_np                      # host mirror (debugging, CPU-side tests)
+        c[_C.CTL_STEP], c[_C.CTL_SAMPLE0], c[_C.CTL_ROW0], c[_C.CTL_LR_BITS] = \
+            step, s0, int(row0), self._lr_cached[1]
+        if self.device.type == 'cuda':
+            _C.call('tn_set_ctl', self._ctl_ptr, step, s0, int(row0), self._lr_cached[1], self._stream())
 
     def _upload_idx(self, ids):
         """Index vector of this step -> self.idx, through the next pinned ring slot (eager copy,
