@@ -103,6 +103,12 @@ __device__ __forceinline__ void stage_pitched(float *dst, const float *__restric
     const int row = (int)dS.div((uint32_t)t);
     dst[row * pitch + (t - row * S)] = __ldg(src + t);
   }
+  // the pad columns are read by the windows of the last image column; what they feed is either
+  // dropped or multiplied by a zero gradient -- and 0 * NaN is NaN, so they must hold zeros, not
+  // whatever the previous kernel left in shared memory
+  const int rows = n / S;
+  for (int r = threadIdx.x; r < rows; r += blockDim.x)
+    for (int c = S; c < pitch; ++c) dst[r * pitch + c] = 0.f;
 }
 
 // ReLU family on this path, literally layer.py:36: max(0,z) + (min(0,z)*NN)/100 with BOTH roundings
@@ -447,8 +453,13 @@ __global__ void __launch_bounds__(kST, 2) small_bwd_kernel(const __grid_constant
       const int pin = p - (int)k.dHH.div((uint32_t)p) * HH;
       const int y = (int)k.dH.div((uint32_t)pin);
       const int yy = y - pd, xx = pin - y * Hp - pd;
-      if (yy < 0 || xx < 0 || yy >= lim || xx >= lim)
+      if (yy < 0 || xx < 0 || yy >= lim || xx >= lim) {
         for (int i = 0; i < ps4; ++i) gz4[p * ps4 + i] = z4;
+      } else if (M < ps) {
+        // interior pixel: the staging writes maps 0..M-1 only; the padded map slots are read by the
+        // input-gradient loop against zero weights -- 0 * NaN is NaN, so they hold zeros
+        for (int m = M; m < ps; ++m) gz[p * ps + m] = 0.f;
+      }
     }
     for (int t = tid; t < k.gg; t += kST) gz[NB * gzimg + t] = 0.f;
     for (int t = tid; t < k.gx; t += kST) xs[NB * CSS + t] = 0.f;
@@ -499,6 +510,13 @@ __global__ void __launch_bounds__(kST, 2) small_bwd_kernel(const __grid_constant
     const int b0 = grp * NB, nb = min(NB, k.B - b0);
     const int ph0 = min(stage_no, 5) * 8;
     stage_contig_async(xs, k.x + (size_t)b0 * CSS, nb * CSS);
+    if (nb < NB) {
+      // ragged last group: the windows of its last image overhang into the NEXT image slot, which
+      // holds whatever an earlier group (or an earlier kernel) left there.  Those products are
+      // multiplied by the zero border of dL/dz -- but 0 * NaN is NaN: give them zeros to read.
+      for (int t = tid; t < k.gx; t += kST) xs[nb * CSS + t] = 0.f;
+      for (int t = tid; t < k.gg; t += kST) gz[nb * gzimg + t] = 0.f;
+    }
     {  // dL/dz of the conv layer, one thread per pooled cell: g = dL/dpooled * act'(pooled) goes to
        // every element of the window that equals the maximum (Theano's MaxPoolGrad)
       const int cell0 = b0 * M * PP;
@@ -769,6 +787,8 @@ __global__ void __launch_bounds__(kST, 2) small_wgrad_kernel(const __grid_consta
     const int ph0 = min(stage_no, 5) * 8;
     if (Sp == S) stage_contig(xs, k.x + (size_t)b0 * CSS, nb * CSS);
     else stage_pitched(xs, k.x + (size_t)b0 * CSS, nb * CSS, S, Sp, k.dS);
+    if (nb < NB)       // ragged last group: zeros, not leftovers, behind its last image (0 * NaN)
+      for (int t = tid; t < k.gx; t += kST) xs[nb * CSSp + t] = 0.f;
     __syncthreads();
     TN_PHASE(ph0 + 2);
     if (wact) {
