@@ -113,7 +113,7 @@ def _facade_worker(rank, world, port, q):
     c = net._ctl_np
     q.put((rank, net.local_bsz, net.batch_sz, net.theta.numpy().copy(),
            (int(c[_C.CTL_STEP]), int(c[_C.CTL_SAMPLE0]), int(c[_C.CTL_ROW0])),
-           float(np.float32(net.cur_learn_rate.get_value()))))
+           float(np.float32(net.cur_learn_rate.get_value())), net._bucket_split(), int(net.n_flat)))
     torch.distributed.destroy_process_group()
 
 
@@ -133,8 +133,11 @@ def test_two_rank_facade_shards_the_batch_and_starts_from_rank0_weights():
     for pr in procs:
         pr.join(timeout=60)
         assert pr.exitcode == 0
-    (r0, l0, b0, th0, ctl0, lr0), (r1, l1, b1, th1, ctl1, lr1) = res
+    (r0, l0, b0, th0, ctl0, lr0, bk0, nf0), (r1, l1, b1, th1, ctl1, lr1, bk1, nf1) = res
     assert (l0, b0, l1, b1) == (8, 16, 8, 16)
+    # gradient bucketing: the trailing dense layers (hidden, softmax) start at layer 5 / flat offset
+    # 36 + 4 + 720 + 20 = 780; everything from there to the end (+ the NLL slot) is the early bucket
+    assert bk0 == bk1 == (5, 780) and nf0 == 780 + 360000 + 500 + 5000 + 12
     assert np.array_equal(th0, th1) and np.abs(th0).max() > 0
     assert ctl0 == (5, 0, 48) and ctl1 == (5, 8, 48)
     assert lr0 == lr1
