@@ -96,45 +96,64 @@ sgd_step_kernel(float *__restrict__ theta, float *__restrict__ vel, const float 
   const float l2x2 = 2.f * sg.l2;
   const bool clip1d = sg.ndim == 1 && sg.maxnorm != 0.f;
   float wsum = 0.f;
-  // data parallel: fetch this thread's 4 elements from every rank up front (4 x W independent
-  // NVLink loads in flight, L1 bypassed: peer data changes every step), then add in rank order
-  float gsum[4] = {0.f, 0.f, 0.f, 0.f};
-  if (from_peers) {
-    float gp[4][kMaxPeers];
+  // One float4 per thread (every tensor starts 16-byte aligned and is padded to a multiple of 4;
+  // pad words are read but never written).
+  // data parallel: the quad comes from every rank (W independent 16-byte NVLink loads in flight,
+  // L1 bypassed: peer data changes every step) and is added in rank order
+  const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+  if (i0 < end) {
+    float4 g4;
+    if (from_peers) {
+      float4 gp[kMaxPeers];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int64_t i = base + q * kUpdThreads + threadIdx.x;
-#pragma unroll
-      for (int r = 0; r < kMaxPeers; ++r) gp[q][r] = (r < W && i < end) ? __ldcg(peers.grad[r] + i) : 0.f;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      gsum[q] = gp[q][0];
+      for (int r = 0; r < kMaxPeers; ++r)
+        if (r < W) gp[r] = __ldcg(reinterpret_cast<const float4 *>(peers.grad[r] + i0));
+      g4 = gp[0];
 #pragma unroll
       for (int r = 1; r < kMaxPeers; ++r)
-        if (r < W) gsum[q] = __fadd_rn(gsum[q], gp[q][r]);
+        if (r < W) {
+          g4.x = __fadd_rn(g4.x, gp[r].x); g4.y = __fadd_rn(g4.y, gp[r].y);
+          g4.z = __fadd_rn(g4.z, gp[r].z); g4.w = __fadd_rn(g4.w, gp[r].w);
+        }
+    } else {
+      g4 = *reinterpret_cast<const float4 *>(grad + i0);
     }
-  }
+    const float4 th4 = *reinterpret_cast<const float4 *>(theta + i0);
+    const float thv[4] = {th4.x, th4.y, th4.z, th4.w};
+    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int64_t i = base + q * kUpdThreads + threadIdx.x;
-    if (i < end) {
-      const float th = theta[i];
-      if (sg.l1 != 0.f) wsum = fmaf(sg.l1, fabsf(th), wsum);
-      if (sg.l2 != 0.f) wsum = fmaf(sg.l2, th * th, wsum);
-      if (sg.rate != 0.f) {
-        const float gi = from_peers ? gsum[q] : grad[i];
-        float g = grad_scale == 1.f ? gi : __fmul_rn(gi, grad_scale);
+    for (int e = 0; e < 4; ++e)
+      if (i0 + e < end) {
+        if (sg.l1 != 0.f) wsum = fmaf(sg.l1, fabsf(thv[e]), wsum);
+        if (sg.l2 != 0.f) wsum = fmaf(sg.l2, thv[e] * thv[e], wsum);
+      }
+    if (sg.rate != 0.f) {
+      const float4 v4 = *reinterpret_cast<const float4 *>(vel + i0);
+      const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+      float vn[4], tn_[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float th = thv[e];
+        float g = grad_scale == 1.f ? gv[e] : __fmul_rn(gv[e], grad_scale);
         if (sg.l1 != 0.f) {
           const float sgn = th > 0.f ? 1.f : (th < 0.f ? -1.f : 0.f);
           g = __fadd_rn(g, __fmul_rn(sg.l1, sgn));
         }
         if (sg.l2 != 0.f) g = __fadd_rn(g, __fmul_rn(l2x2, th));
-        const float v = vel[i];
-        vel[i] = __fadd_rn(__fmul_rn(m, v), __fmul_rn(om, g));
-        float tn_ = __fsub_rn(th, __fmul_rn(step, v));
-        if (clip1d) tn_ = fminf(fmaxf(tn_, -sg.maxnorm), sg.maxnorm);
-        theta[i] = tn_;
+        vn[e] = __fadd_rn(__fmul_rn(m, vv[e]), __fmul_rn(om, g));
+        tn_[e] = __fsub_rn(th, __fmul_rn(step, vv[e]));
+        if (clip1d) tn_[e] = fminf(fmaxf(tn_[e], -sg.maxnorm), sg.maxnorm);
+      }
+      if (i0 + 3 < end) {
+        *reinterpret_cast<float4 *>(vel + i0) = make_float4(vn[0], vn[1], vn[2], vn[3]);
+        *reinterpret_cast<float4 *>(theta + i0) = make_float4(tn_[0], tn_[1], tn_[2], tn_[3]);
+      } else {                                   // last quad of a tensor: its pad words stay untouched
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (i0 + e < end) {
+            vel[i0 + e] = vn[e];
+            theta[i0 + e] = tn_[e];
+          }
       }
     }
   }
