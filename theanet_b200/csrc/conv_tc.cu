@@ -446,13 +446,18 @@ colsum_bf16_kernel(const __nv_bfloat16 *__restrict__ gz, int64_t P, int M,
     partial[(size_t)blockIdx.x * M + m] = t;
   }
 }
+// one warp per channel: the lanes walk the slices, then a fixed-order shuffle tree (a thread per
+// channel adding 296 slices one after the other took 20 us)
 __global__ void colsum_finish_kernel(const float *__restrict__ partial, int nslices, int M,
                                      float *__restrict__ db) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   float s = 0.f;
-  for (int k = 0; k < nslices; ++k) s += partial[(size_t)k * M + m];
-  db[m] = s;
+  for (int k = lane; k < nslices; k += 32) s += partial[(size_t)k * M + m];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) db[m] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -930,7 +935,7 @@ extern "C" int tn_conv2d_tc_wgrad(const void *x, const void *gz, float *dW, floa
   colsum_bf16_kernel<<<kColSlices, 1024, 0, st>>>((const __nv_bfloat16 *)gz,
                                                    (int64_t)B * out_sz * out_sz, M, cpart);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(db partial)");
-  colsum_finish_kernel<<<ceil_div(M, 128), 128, 0, st>>>(cpart, kColSlices, M, db);
+  colsum_finish_kernel<<<ceil_div(M, 8), 256, 0, st>>>(cpart, kColSlices, M, db);
   TN_LAUNCH_CHECK("tn_conv2d_tc_wgrad(db)");
   return TN_OK;
 }

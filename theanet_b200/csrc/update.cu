@@ -211,31 +211,40 @@ __device__ __forceinline__ float maxnorm_scale(float sumsq, float maxnorm) {
   return __fdiv_rn(__fadd_rn(1e-7f, d), __fadd_rn(1e-7f, n));
 }
 
-// 2-D (rows x cols): per-column norm over axis 0; 32 columns x 8 row-slices per CTA
-__global__ void maxnorm_cols_kernel(float *__restrict__ w, int rows, int cols, float maxnorm) {
-  __shared__ float red[8][33];
-  __shared__ float scale[32];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + tx;
+// 2-D (rows x cols): per-column norm over axis 0; 8 columns (one 32-byte sector per row) x 128 row
+// slices per CTA: cols/8 CTAs of 1024 threads (the first version ran 32 columns x 8 slices, i.e. 32
+// CTAs of 256 threads for a 4096 x 1024 matrix, and took longer than the update itself)
+constexpr int kMnCols = 8, kMnSlices = 128;
+__global__ void __launch_bounds__(kMnCols * kMnSlices)
+maxnorm_cols_kernel(float *__restrict__ w, int rows, int cols, float maxnorm) {
+  __shared__ float red[kMnSlices / 4][kMnCols];
+  __shared__ float scale[kMnCols];
+  const int tx = threadIdx.x & (kMnCols - 1), ty = threadIdx.x / kMnCols;
+  const int c = blockIdx.x * kMnCols + tx;
   float s = 0.f;
-  if (c < cols)
-    for (int r = ty; r < rows; r += 8) {
+  if (c < cols) {
+#pragma unroll 4
+    for (int r = ty; r < rows; r += kMnSlices) {
       const float v = w[(size_t)r * cols + c];
       s = fmaf(v, v, s);
     }
-  red[ty][tx] = s;
+  }
+  // a warp holds 4 row slices x 8 columns: fold the slices (fixed order), then the 32 warps
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  if ((threadIdx.x & 31) < kMnCols) red[threadIdx.x >> 5][tx] = s;
   __syncthreads();
-  if (ty == 0) {
+  if (threadIdx.x < kMnCols) {
     float t = red[0][tx];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) t += red[q][tx];
+    for (int q = 1; q < kMnSlices / 4; ++q) t += red[q][tx];
     scale[tx] = maxnorm_scale(t, maxnorm);
   }
   __syncthreads();
   if (c < cols) {
     const float sc = scale[tx];
     if (sc != 1.f)
-      for (int r = ty; r < rows; r += 8) w[(size_t)r * cols + c] *= sc;
+      for (int r = ty; r < rows; r += kMnSlices) w[(size_t)r * cols + c] *= sc;
   }
 }
 
@@ -316,8 +325,8 @@ static int update_impl(float *theta, float *vel, const float *grad, const tn_par
     const tn_param_seg &sg = segs[s];
     if (sg.maxnorm == 0.f || sg.rate == 0.f || sg.ndim == 1) continue;
     if (sg.ndim == 2) {
-      maxnorm_cols_kernel<<<ceil_div(sg.cols, 32), 256, 0, st>>>(theta + sg.offset, sg.rows,
-                                                                 sg.cols, sg.maxnorm);
+      maxnorm_cols_kernel<<<ceil_div(sg.cols, kMnCols), kMnCols * kMnSlices, 0, st>>>(
+          theta + sg.offset, sg.rows, sg.cols, sg.maxnorm);
     } else {
       maxnorm_rows_kernel<<<ceil_div(sg.rows, 8), 256, 0, st>>>(theta + sg.offset, sg.rows,
                                                                 sg.cols, sg.maxnorm);
