@@ -262,13 +262,14 @@ def profile_stages(net, fn, nb, reps):
     counter = {}
 
     def timed_call(name, *a):
-        k = counter.get(name, 0)
-        counter[name] = k + 1
+        key = name[:-3] if name.endswith('_sm') else name     # tn_dense_bwd_*_sm: same product, SM-bounded
+        k = counter.get(key, 0)
+        counter[key] = k + 1
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         orig(name, *a)
         e.record()
-        records.setdefault((name, k), []).append((s, e))
+        records.setdefault((key, k), []).append((s, e))
 
     import theanet_b200.neuralnet as nnmod
     saved, saved_ov = net.use_graph, net.overlap_wgrad
