@@ -413,3 +413,39 @@ def test_meanlayer_colorlayer_and_aux_restatements():
     assert abs(cost - loss.item()) < 1e-12
     for got, want_t in zip(on.last_grads[1] + on.last_grads[3], (W, b, Ws, bs)):
         assert np.allclose(got, want_t.grad.numpy(), atol=1e-12)
+
+
+def test_kink_localisation_hook_only_touches_elements_at_the_kink():
+    """OracleNet.kink_source (tests/test_gpu_net.py::run_pair): with the oracle's OWN hidden output as
+    the source nothing is re-signed; flipping the sign of one tiny pre-activation in the source is
+    recorded as exactly one flip whose |z| is what it was, and moves only that unit's gradient."""
+    import copy
+    layers = [('InputLayer', {'img_sz': 6, 'num_maps': 1}),
+              ('HiddenLayer', {'n_out': 16, 'pdrop': 0, 'actvn': 'relu10'}),
+              ('SoftmaxLayer', {'n_out': 5})]
+    tp = {'BATCH_SZ': 8, 'NUM_EPOCHS': 1, 'EPOCHS_TO_TEST': 1, 'TEST_SAMP_SZ': 8, 'INIT_LEARNING_RATE': .1,
+          'EPOCHS_TO_HALF_RATE': 1, 'SEED': 3}
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((8, 1, 6, 6)).astype(np.float32)
+    y = rng.integers(0, 5, 8)
+    a = O.OracleNet(copy.deepcopy(layers), dict(tp))
+    a.train_step(x, y, step=0, apply_update=False)
+    base = [g.copy() for g in a.last_grads[1]]
+    out = a.last_caches[1]['out'].copy()
+    z = a.last_caches[1]['z']
+    b = O.OracleNet(copy.deepcopy(layers), dict(tp))
+    b.kink_source = {1: out}
+    b.train_step(x, y, step=0, apply_update=False)
+    assert b.kink_flips == [(1, 0, 0.0, float(np.abs(z).max()))]
+    assert all(np.array_equal(u, v) for u, v in zip(base, b.last_grads[1]))
+    # the other implementation landed on the other side of zero for the smallest |z|
+    i, j = np.unravel_index(np.argmin(np.abs(z)), z.shape)
+    other = out.copy()
+    other[i, j] = -np.sign(z[i, j]) * 1e-9
+    c = O.OracleNet(copy.deepcopy(layers), dict(tp))
+    c.kink_source = {1: other}
+    c.train_step(x, y, step=0, apply_update=False)
+    (li, n, zflip, zmax), = c.kink_flips
+    assert (li, n) == (1, 1) and np.isclose(zflip, abs(z[i, j])) and zmax == float(np.abs(z).max())
+    dW = c.last_grads[1][0] - base[0]
+    assert np.any(dW[:, j] != 0) and not np.any(np.delete(dW, j, axis=1))
