@@ -1,6 +1,11 @@
 // HiddenLayer matrix products on the 5th-generation tensor cores (theanet/layer/hidden.py:30-32
 // tt.dot and its two gradients via tt.grad, layer.py:83).
 //
+// Two kernels live here.  gemm_tc_sk_kernel (further down: cluster split-K, partial tiles exchanged
+// over distributed shared memory) is the default float32 path since round 2; gemm_tc_kernel, the
+// first generation described next, serves the single-pass TF32 mode and stays as the A/B reference
+// (tn_set_dense_mode).  Both share the tile formats, the epilogue and the host-side tensor maps.
+//
 // One warp-specialised kernel serves out = x.W, dx = g.W^T and dW = x^T.g:
 //   warps 0..3  : TMA producers -- cp.async.bulk.tensor tiles (128-byte swizzle) into a ring of
 //                 shared-memory stages, completion on mbarriers; k-blocks round-robin;
